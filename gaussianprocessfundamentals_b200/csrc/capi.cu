@@ -1,0 +1,371 @@
+// C-ABI of libgpb (see include/gpb.h).  Host-side only: argument checking, workspace layout, launch sequencing.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gpb.h"
+#include "internal.h"
+#include "program.cuh"
+
+namespace gpb {
+std::atomic<long long> g_launches{0};
+}  // namespace gpb
+
+static thread_local std::string g_err;
+static int fail_arg(int k, const char* what) {
+  g_err = std::string("invalid argument ") + std::to_string(k) + ": " + what;
+  return -k;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return 1000 + (int)e;
+}
+#define CU(x, where) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, where); } while (0)
+
+static bool g_inited = false;
+static int ensure_init() {
+  if (g_inited) return 0;
+  CU(gpb::linalg_init(), "linalg_init");
+  CU(gpb::assemble_init(), "assemble_init");
+  g_inited = true;
+  return 0;
+}
+
+struct gpb_program {
+  int n_ops, dim, cp_mode, n_hp;
+  std::vector<int32_t> code;
+  int32_t* code_dev;
+};
+
+enum { NBUF = 11 };
+struct PlanMat {
+  int64_t n;
+  int ld, nblk, n_hp, n_gtiles;
+  size_t off[NBUF], bytes[NBUF];
+  size_t off_wd, off_part, off_gpart, off_tmpv;
+};
+
+struct gpb_plan {
+  int B, want_grad;
+  std::vector<PlanMat> mats;
+  std::vector<const gpb_program*> progs;
+  size_t ws_bytes, off_desc, off_in, in_bytes, off_out, out_bytes;
+  size_t off_hp_all, off_noise_all, off_nll_all, off_grad_all, off_info_all;
+  std::vector<size_t> hp_prefix, grad_prefix;
+  char* ws;
+  int n_max, n_hp_max, n_ops_max, dim;
+  gpb::Exec ex;
+  bool own_streams;
+  char* h_in;   // pinned mirror of the small input region
+  char* h_out;  // pinned mirror of the small output region
+};
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" {
+
+int gpb_version(void) { return 100; }
+const char* gpb_last_error(void) { return g_err.c_str(); }
+long long gpb_launch_count(void) { return gpb::g_launches.load(); }
+
+int gpb_program_create(const int32_t* code, int n_ops, int dim, int cp_mode, gpb_program_t** out) {
+  if (!code) return fail_arg(1, "code is null");
+  if (n_ops <= 0 || n_ops > GPB_MAX_OPS) return fail_arg(2, "n_ops out of range");
+  if (dim < 1 || dim > GPB_MAX_DIM) return fail_arg(3, "dim out of range");
+  if (cp_mode < 0 || cp_mode > 2) return fail_arg(4, "cp_mode out of range");
+  if (!out) return fail_arg(5, "out is null");
+  int sp = 0, tape = 0, max_sp = 0, n_hp = 0;
+  for (int pc = 0; pc < n_ops; ++pc) {
+    const int32_t* w = code + pc * GPB_OP_WORDS;
+    const int op = w[0];
+    if (op >= GPB_OP_SE && op <= GPB_OP_SE_ARD) {
+      const int nq = gpb_leaf_nhp(op, w[2], dim);
+      if (w[1] < 0) return fail_arg(1, "negative hyper-parameter offset");
+      if (w[1] + nq > n_hp) n_hp = w[1] + nq;
+      tape += nq;
+      ++sp;
+    } else if (op == GPB_OP_ADD2 || op == GPB_OP_MUL2) {
+      if (sp < 2) return fail_arg(1, "stack underflow");
+      --sp;
+      if (op == GPB_OP_MUL2) tape += 2;
+    } else if (op == GPB_OP_CPW) {
+      if (sp < 1) return fail_arg(1, "stack underflow");
+      if (dim != 1) return fail_arg(3, "change-point operators need 1-d inputs (Operators.py:398)");
+      if (w[3] < 2 || w[2] < 0 || w[2] >= w[3]) return fail_arg(1, "bad change-point child index");
+      if (w[1] + w[3] - 1 > n_hp) n_hp = w[1] + w[3] - 1;
+      tape += 4;
+    } else {
+      return fail_arg(1, "unknown opcode");
+    }
+    if (sp > max_sp) max_sp = sp;
+  }
+  if (sp != 1) return fail_arg(1, "program does not leave exactly one value");
+  if (max_sp > GPB_MAX_STACK) return fail_arg(1, "operand stack too deep");
+  if (tape > GPB_MAX_TAPE) return fail_arg(1, "gradient tape too long");
+  if (n_hp > GPB_MAX_HP) return fail_arg(1, "too many hyper-parameters");
+  int rc = ensure_init();
+  if (rc) return rc;
+  gpb_program* p = new gpb_program;
+  p->n_ops = n_ops; p->dim = dim; p->cp_mode = cp_mode; p->n_hp = n_hp;
+  p->code.assign(code, code + (size_t)n_ops * GPB_OP_WORDS);
+  p->code_dev = nullptr;
+  cudaError_t e = cudaMalloc(&p->code_dev, p->code.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(p->code_dev, p->code.data(), p->code.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { if (p->code_dev) cudaFree(p->code_dev); delete p; return fail_cuda(e, "gpb_program_create"); }
+  *out = p;
+  return 0;
+}
+
+int gpb_program_num_hp(const gpb_program_t* prog) { return prog ? prog->n_hp : -1; }
+
+void gpb_program_destroy(gpb_program_t* prog) {
+  if (!prog) return;
+  if (prog->code_dev) cudaFree(prog->code_dev);
+  delete prog;
+}
+
+int gpb_assemble(const gpb_program_t* prog, const double* X, const double* X2, int64_t n, int64_t m,
+                 const double* hp, const double* noise, double* K, int64_t ldk, int lower_only, void* stream) {
+  if (!prog) return fail_arg(1, "program is null");
+  if (!X) return fail_arg(2, "X is null");
+  if (n < 0) return fail_arg(4, "n < 0");
+  if (m < 0) return fail_arg(5, "m < 0");
+  if (!hp && prog->n_hp > 0) return fail_arg(6, "hp is null");
+  if (!K) return fail_arg(8, "K is null");
+  if (ldk < n) return fail_arg(9, "ldk < n");
+  if (lower_only && (X2 || n != m)) return fail_arg(10, "lower_only needs the symmetric case");
+  if (n == 0 || m == 0) return 0;
+  CU(gpb::run_assemble_rect(prog->code_dev, prog->n_ops, prog->dim, prog->cp_mode, X, X2, n, m, hp, prog->n_hp, noise,
+                            K, ldk, lower_only, (cudaStream_t)stream), "gpb_assemble");
+  return 0;
+}
+
+int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb_plan_t** out) {
+  if (B <= 0) return fail_arg(1, "B <= 0");
+  if (!progs) return fail_arg(2, "progs is null");
+  if (!n) return fail_arg(3, "n is null");
+  if (!out) return fail_arg(5, "out is null");
+  int rc = ensure_init();
+  if (rc) return rc;
+  gpb_plan* p = new gpb_plan;
+  p->B = B; p->want_grad = want_grad ? 1 : 0; p->ws = nullptr;
+  p->n_max = 0; p->n_hp_max = 0; p->n_ops_max = 0; p->dim = progs[0] ? progs[0]->dim : 1;
+  p->mats.resize(B); p->progs.assign(progs, progs + B);
+  p->hp_prefix.resize(B + 1); p->grad_prefix.resize(B + 1);
+  p->hp_prefix[0] = 0; p->grad_prefix[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    if (!progs[b]) { delete p; return fail_arg(2, "null program"); }
+    if (n[b] < 1 || n[b] > (1 << 20)) { delete p; return fail_arg(3, "n out of range"); }
+    if (progs[b]->dim != p->dim) { delete p; return fail_arg(2, "all programs of a plan must share dim"); }
+    p->hp_prefix[b + 1] = p->hp_prefix[b] + progs[b]->n_hp;
+    p->grad_prefix[b + 1] = p->grad_prefix[b] + progs[b]->n_hp + 1;
+    if (n[b] > p->n_max) p->n_max = (int)n[b];
+    if (progs[b]->n_hp > p->n_hp_max) p->n_hp_max = progs[b]->n_hp;
+    if (progs[b]->n_ops > p->n_ops_max) p->n_ops_max = progs[b]->n_ops;
+  }
+  size_t off = 0;
+  p->off_desc = off; off = al(off + (size_t)B * sizeof(GpbMat));
+  p->off_in = off;
+  p->off_hp_all = off; off += p->hp_prefix[B] * 8;
+  p->off_noise_all = off; off += (size_t)B * 8;
+  p->in_bytes = off - p->off_in; off = al(off);
+  p->off_out = off;
+  p->off_nll_all = off; off += (size_t)B * 8;
+  p->off_grad_all = off; off += p->grad_prefix[B] * 8;
+  p->off_info_all = off; off += (size_t)B * 4;
+  p->out_bytes = off - p->off_out; off = al(off);
+  for (int b = 0; b < B; ++b) {
+    PlanMat& m = p->mats[b];
+    const gpb_program* g = progs[b];
+    m.n = n[b];
+    m.ld = (int)((n[b] + 1 + 7) / 8 * 8);
+    m.nblk = (int)((n[b] + GPB_NB - 1) / GPB_NB);
+    m.n_hp = g->n_hp;
+    m.n_gtiles = gpb::grad_tiles((int)n[b]);
+    auto put = [&](int which, size_t bytes) { m.off[which] = off; m.bytes[which] = bytes; off = al(off + bytes); };
+    put(GPB_BUF_X, (size_t)n[b] * g->dim * 8);
+    put(GPB_BUF_Y, (size_t)n[b] * 8);
+    put(GPB_BUF_ALPHA, (size_t)n[b] * 8);
+    put(GPB_BUF_Z, (size_t)n[b] * 8);
+    m.off_tmpv = off; off = al(off + (size_t)n[b] * 8);
+    m.off_part = off; off = al(off + (size_t)m.nblk * 8);
+    m.off_wd = off; off = al(off + (size_t)m.nblk * GPB_NB * GPB_NB * 8);
+    m.off_gpart = off; off = al(off + (want_grad ? (size_t)m.n_gtiles * (g->n_hp + 1) * 8 : 0));
+    put(GPB_BUF_A, (size_t)m.ld * (n[b] + 1) * 8);
+    put(GPB_BUF_KINV, want_grad ? (size_t)m.ld * n[b] * 8 : 0);
+    m.off[GPB_BUF_HP] = p->off_hp_all + p->hp_prefix[b] * 8; m.bytes[GPB_BUF_HP] = (size_t)g->n_hp * 8;
+    m.off[GPB_BUF_NOISE] = p->off_noise_all + (size_t)b * 8; m.bytes[GPB_BUF_NOISE] = 8;
+    m.off[GPB_BUF_NLL] = p->off_nll_all + (size_t)b * 8; m.bytes[GPB_BUF_NLL] = 8;
+    m.off[GPB_BUF_GRAD] = p->off_grad_all + p->grad_prefix[b] * 8; m.bytes[GPB_BUF_GRAD] = (size_t)(g->n_hp + 1) * 8;
+    m.off[GPB_BUF_INFO] = p->off_info_all + (size_t)b * 4; m.bytes[GPB_BUF_INFO] = 4;
+  }
+  p->ws_bytes = off;
+  p->h_in = nullptr; p->h_out = nullptr;
+  cudaError_t e = cudaMallocHost(&p->h_in, p->in_bytes + 16);
+  if (e == cudaSuccess) e = cudaMallocHost(&p->h_out, p->out_bytes + 16);
+  p->own_streams = false;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->ex.side, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&p->ex.ev_e[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_g[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { delete p; return fail_cuda(e, "gpb_plan_create"); }
+  p->own_streams = true;
+  *out = p;
+  return 0;
+}
+
+size_t gpb_plan_workspace_bytes(const gpb_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
+
+int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (!workspace || ((uintptr_t)workspace & 255)) return fail_arg(2, "workspace null or not 256-byte aligned");
+  p->ws = (char*)workspace;
+  std::vector<GpbMat> h(p->B);
+  for (int b = 0; b < p->B; ++b) {
+    const PlanMat& m = p->mats[b];
+    const gpb_program* g = p->progs[b];
+    GpbMat& d = h[b];
+    memset(&d, 0, sizeof(d));
+    char* w = p->ws;
+    d.A = (double*)(w + m.off[GPB_BUF_A]);
+    d.Kinv = p->want_grad ? (double*)(w + m.off[GPB_BUF_KINV]) : nullptr;
+    d.Wd = (double*)(w + m.off_wd);
+    d.part = (double*)(w + m.off_part);
+    d.gpart = (double*)(w + m.off_gpart);
+    d.alpha = (double*)(w + m.off[GPB_BUF_ALPHA]);
+    d.zvec = (double*)(w + m.off[GPB_BUF_Z]);
+    d.tmpv = (double*)(w + m.off_tmpv);
+    d.X = (const double*)(w + m.off[GPB_BUF_X]);
+    d.y = (const double*)(w + m.off[GPB_BUF_Y]);
+    d.hp = (const double*)(w + m.off[GPB_BUF_HP]);
+    d.noise = (const double*)(w + m.off[GPB_BUF_NOISE]);
+    d.code = g->code_dev;
+    d.nll = (double*)(w + m.off[GPB_BUF_NLL]);
+    d.grad = (double*)(w + m.off[GPB_BUF_GRAD]);
+    d.info = (int*)(w + m.off[GPB_BUF_INFO]);
+    d.n = (int)m.n; d.ld = m.ld; d.dim = g->dim; d.n_ops = g->n_ops; d.n_hp = g->n_hp; d.aug = 1;
+    d.cp_mode = g->cp_mode; d.n_gtiles = m.n_gtiles;
+  }
+  CU(cudaMemcpy(p->ws + p->off_desc, h.data(), (size_t)p->B * sizeof(GpbMat), cudaMemcpyHostToDevice), "gpb_plan_bind");
+  CU(cudaMemset(p->ws + p->off_out, 0, p->out_bytes), "gpb_plan_bind");
+  return 0;
+}
+
+int gpb_plan_buffer(const gpb_plan_t* p, int b, int which, void** ptr, size_t* bytes, int64_t* ld) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (b < 0 || b >= p->B) return fail_arg(2, "b out of range");
+  if (which < 0 || which >= NBUF) return fail_arg(3, "unknown buffer");
+  if (!p->ws) return fail_arg(1, "plan is not bound");
+  const PlanMat& m = p->mats[b];
+  if (ptr) *ptr = p->ws + m.off[which];
+  if (bytes) *bytes = m.bytes[which];
+  if (ld) *ld = m.ld;
+  return 0;
+}
+
+int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (!p->ws) return fail_arg(1, "plan is not bound");
+  if ((stages & (GPB_STAGE_INVERSE | GPB_STAGE_GRAD)) && !p->want_grad)
+    return fail_arg(2, "plan was created without gradient workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
+  p->ex.main = s;
+  if (stages & GPB_STAGE_ASSEMBLE) {
+    CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, (size_t)p->B * 4, s), "reset info");
+    CU(gpb::run_assemble_batched(dm, p->B, p->n_max, s), "assemble");
+  }
+  if (stages & GPB_STAGE_POTRF) {
+    const bool lookahead = (p->B == 1 && p->n_max >= 1024);
+    CU(gpb::run_potrf(dm, p->B, p->n_max, 1, lookahead, p->ex), "potrf");
+  }
+  if (stages & GPB_STAGE_NLL) {
+    const double log2pi = std::log(M_PI * 2.0);
+    CU(gpb::run_finalize(dm, p->B, log2pi, s), "finalize");
+  }
+  if (stages & GPB_STAGE_BACKSOLVE) CU(gpb::run_trsv(dm, p->B, p->n_max, 1, s), "backsolve");
+  if (stages & GPB_STAGE_INVERSE) {
+    CU(gpb::run_trtri(dm, p->B, p->n_max, s), "trtri");
+    CU(gpb::run_alpha(dm, p->B, p->n_max, s), "alpha");
+    CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
+  }
+  if (stages & GPB_STAGE_GRAD) CU(gpb::run_grad(dm, p->B, p->n_max, p->n_hp_max, p->n_ops_max, p->dim, s), "grad");
+  return 0;
+}
+
+int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, const double* const* y_host,
+                       const double* const* hp_host, const double* noise_host, double* nll_host, double* grad_host,
+                       int* info_host, void* stream) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (!p->ws) return fail_arg(1, "plan is not bound");
+  if (!hp_host && p->hp_prefix[p->B] > 0) return fail_arg(5, "hp_host is null");
+  if (!noise_host) return fail_arg(6, "noise_host is null");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int b = 0; b < p->B; ++b) {
+    const PlanMat& m = p->mats[b];
+    if (X_host && X_host[b])
+      CU(cudaMemcpyAsync(p->ws + m.off[GPB_BUF_X], X_host[b], m.bytes[GPB_BUF_X], cudaMemcpyHostToDevice, s), "H2D X");
+    if (y_host && y_host[b])
+      CU(cudaMemcpyAsync(p->ws + m.off[GPB_BUF_Y], y_host[b], m.bytes[GPB_BUF_Y], cudaMemcpyHostToDevice, s), "H2D y");
+    if (m.n_hp > 0) memcpy(p->h_in + (p->off_hp_all - p->off_in) + p->hp_prefix[b] * 8, hp_host[b], (size_t)m.n_hp * 8);
+  }
+  memcpy(p->h_in + (p->off_noise_all - p->off_in), noise_host, (size_t)p->B * 8);
+  CU(cudaMemcpyAsync(p->ws + p->off_in, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, s), "H2D hp");
+  int rc = gpb_plan_eval(p, stages, stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(p->h_out, p->ws + p->off_out, p->out_bytes, cudaMemcpyDeviceToHost, s), "D2H results");
+  CU(cudaStreamSynchronize(s), "sync");
+  if (nll_host) memcpy(nll_host, p->h_out + (p->off_nll_all - p->off_out), (size_t)p->B * 8);
+  if (grad_host) memcpy(grad_host, p->h_out + (p->off_grad_all - p->off_out), p->grad_prefix[p->B] * 8);
+  if (info_host) memcpy(info_host, p->h_out + (p->off_info_all - p->off_out), (size_t)p->B * 4);
+  return 0;
+}
+
+void gpb_plan_destroy(gpb_plan_t* p) {
+  if (!p) return;
+  if (p->own_streams) {
+    cudaStreamDestroy(p->ex.side);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); }
+    cudaEventDestroy(p->ex.ev_join);
+  }
+  if (p->h_in) cudaFreeHost(p->h_in);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  delete p;
+}
+
+int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+             int M, int N, int K, double alpha, double beta, void* stream) {
+  if (!A) return fail_arg(3, "A is null");
+  if (!B) return fail_arg(5, "B is null");
+  if (!C) return fail_arg(7, "C is null");
+  if ((lda & 1) || (ldb & 1)) return fail_arg(4, "leading dimensions of the operands must be even (16-byte cp.async)");
+  if (((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return fail_arg(3, "operands must be 16-byte aligned");
+  if (M <= 0 || N <= 0 || K < 0) return fail_arg(9, "bad shape");
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(gpb::run_gemm_plain(a_kmajor, b_kmajor, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, (cudaStream_t)stream), "gpb_gemm");
+  return 0;
+}
+
+int gpb_microbench(int kind, int iters, int blocks, void* stream) {
+  CU(gpb::run_microbench(kind, iters, blocks, (cudaStream_t)stream), "gpb_microbench");
+  return 0;
+}
+
+int gpb_zero_upper(double* A, int n, int ld, void* stream) {
+  if (!A) return fail_arg(1, "A is null");
+  CU(gpb::run_zero_upper(A, n, ld, (cudaStream_t)stream), "gpb_zero_upper");
+  return 0;
+}
+int gpb_symmetrize(double* A, int n, int ld, void* stream) {
+  if (!A) return fail_arg(1, "A is null");
+  CU(gpb::run_symmetrize(A, n, ld, (cudaStream_t)stream), "gpb_symmetrize");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Host-side launchers shared between the translation units of libgpb (not part of the public C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace gpb {
+
+extern std::atomic<long long> g_launches;  // kernels launched since load (gpb_launch_count)
+
+struct Exec {
+  cudaStream_t main;
+  cudaStream_t side;       // look-ahead stream of the single-matrix Cholesky
+  cudaEvent_t ev_e[2];     // panel k ready (recorded on main)
+  cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side)
+  cudaEvent_t ev_join;
+};
+
+// ---- linalg.cu ------------------------------------------------------------------------------------------------
+cudaError_t run_potrf(const GpbMat* dmats, int B, int n_max, int aug, bool lookahead, const Exec& ex);
+cudaError_t run_finalize(const GpbMat* dmats, int B, double log2pi, cudaStream_t s);
+cudaError_t run_trtri(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
+cudaError_t run_alpha(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
+cudaError_t run_lauum(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
+cudaError_t run_trsv(const GpbMat* dmats, int B, int n_max, int transposed, cudaStream_t s);
+cudaError_t run_zero_upper(double* A, int n, int ld, cudaStream_t s);
+cudaError_t run_symmetrize(double* A, int n, int ld, cudaStream_t s);
+cudaError_t run_gemm_plain(int akm, int bkm, const double* A, int lda, const double* Bm, int ldb, double* C, int ldc,
+                           int M, int N, int K, double alpha, double beta, cudaStream_t s);
+cudaError_t run_microbench(int kind, int iters, int blocks, cudaStream_t s);
+cudaError_t linalg_init();
+
+// ---- assemble.cu ----------------------------------------------------------------------------------------------
+cudaError_t run_assemble_batched(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
+cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int cp_mode, const double* X,
+                              const double* X2, long long n, long long m, const double* hp_dev, int n_hp,
+                              const double* noise_dev, double* K, long long ldk, int lower_only, cudaStream_t s);
+cudaError_t run_grad(const GpbMat* dmats, int B, int n_max, int n_hp_max, int n_ops_max, int dim, cudaStream_t s);
+int grad_tiles(int n);
+cudaError_t assemble_init();
+
+}  // namespace gpb

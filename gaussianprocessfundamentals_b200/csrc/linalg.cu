@@ -1,0 +1,543 @@
+// Dense FP64 linear algebra of the exact-GP likelihood path, batched over independent GPs.
+//
+//   run_potrf    blocked right-looking Cholesky of K + s2*I (Statistics/CovarianceMatrix.py:247-254, :469-479) with the
+//                targets y carried as an extra row, so that L^-1 y (:256-265) and y^T K^-1 y
+//                (Metrics/LogLikelihood.py:39) fall out of the factorisation, and sum(log diag L)
+//                (Metrics/Metrics.py:152-154) is reduced by the diagonal-block kernel.
+//   run_trtri    W = L^-1 by recursive doubling (pure GEMM), run_lauum  K^-1 = W^T W, run_alpha  alpha = W^T z:
+//                the pieces of dNLL/dK = 1/2 (K^-1 - alpha alpha^T) that TF's Cholesky gradient produces for
+//                Optimizer/Fitter.py:124-158.
+//   run_trsv     standalone forward/back substitution (CovarianceMatrix.py:260-262) for get_L_alpha().
+#include "gemm.cuh"
+#include "internal.h"
+
+namespace gpb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMM geometries
+// ---------------------------------------------------------------------------------------------------------------
+
+// trailing update of step k: A[r0:, r0:] -= P P^T with P = A[r0:, k*128 : (k+1)*128], lower tiles, tile columns
+// restricted to [c_lo, c_hi) so that the look-ahead driver can split the update across streams.
+struct GeoSyrk {
+  const GpbMat* mats;
+  int k, c_lo, c_hi;
+  __device__ bool operator()(TileJob& J) const {
+    const GpbMat& d = mats[blockIdx.z];
+    const int nrows = d.n + d.aug;
+    const int r0 = (k + 1) * GPB_NB;
+    if (r0 >= nrows || (k + 1) * GPB_NB > d.n) return false;
+    const int T = (nrows - r0 + GPB_NB - 1) / GPB_NB;
+    int ti, tj;
+    if (!tri_map(blockIdx.x, T, c_lo, c_hi, ti, tj)) return false;
+    const size_t ld = d.ld;
+    const double* P = d.A + (size_t)k * GPB_NB * ld;
+    J.A = P + r0 + ti * GPB_NB;
+    J.B = P + r0 + tj * GPB_NB;
+    J.C = d.A + (r0 + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(GPB_NB, nrows - r0 - ti * GPB_NB);
+    J.nrem = min(GPB_NB, nrows - r0 - tj * GPB_NB);
+    J.klo = 0; J.khi = GPB_NB;
+    J.alpha = -1.0; J.beta = 1.0;
+    return true;
+  }
+};
+
+// panel solve of step k as a product with the inverted diagonal block: A[r0:, kblk] = A[r0:, kblk] * Wd_k^T
+struct GeoPanel {
+  const GpbMat* mats;
+  int k;
+  __device__ bool operator()(TileJob& J) const {
+    const GpbMat& d = mats[blockIdx.z];
+    const int nrows = d.n + d.aug;
+    const int r0 = (k + 1) * GPB_NB;
+    if (r0 > d.n) return false;  // block k is not a full pivot block
+    const int i0 = r0 + blockIdx.x * GPB_NB;
+    if (i0 >= nrows) return false;
+    const size_t ld = d.ld;
+    double* P = d.A + (size_t)k * GPB_NB * ld + i0;
+    J.A = P; J.C = P;
+    J.B = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+    J.lda = J.ldc = d.ld; J.ldb = GPB_NB;
+    J.mrem = min(GPB_NB, nrows - i0);
+    J.nrem = GPB_NB;
+    J.klo = 0; J.khi = GPB_NB;
+    J.alpha = 1.0; J.beta = 0.0;
+    return true;
+  }
+};
+
+// triangular inverse by recursive doubling, level s: sub-problem p owns the 2s x 2s diagonal block at r0 = 2 s p
+//   [W11 0; L21 W22]  ->  W21 = -W22 * (L21 * W11)
+// phase T:  T = L21 * W11   (NN, k >= tile column start because W11 is lower triangular)   -> Kinv scratch
+struct GeoTrtriT {
+  const GpbMat* mats;
+  int s;
+  __device__ bool operator()(TileJob& J) const {
+    const GpbMat& d = mats[blockIdx.z];
+    const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
+    if (rA >= d.n) return false;
+    const int M = min(s, d.n - rA);
+    const int ts = s / GPB_NB;
+    const int ti = blockIdx.x / ts, tj = blockIdx.x % ts;
+    if (ti * GPB_NB >= M) return false;
+    const size_t ld = d.ld;
+    J.A = d.A + (rA + ti * GPB_NB) + (size_t)r0 * ld;
+    J.B = d.A + r0 + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.C = d.Kinv + (rA + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(GPB_NB, M - ti * GPB_NB);
+    J.nrem = GPB_NB;
+    J.klo = tj * GPB_NB; J.khi = s;
+    J.alpha = 1.0; J.beta = 0.0;
+    return true;
+  }
+};
+// phase W:  W21 = -W22 * T   (NN, k <= tile row end because W22 is lower triangular)
+struct GeoTrtriW {
+  const GpbMat* mats;
+  int s;
+  __device__ bool operator()(TileJob& J) const {
+    const GpbMat& d = mats[blockIdx.z];
+    const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
+    if (rA >= d.n) return false;
+    const int M = min(s, d.n - rA);
+    const int ts = s / GPB_NB;
+    const int ti = blockIdx.x / ts, tj = blockIdx.x % ts;
+    if (ti * GPB_NB >= M) return false;
+    const size_t ld = d.ld;
+    J.A = d.A + (rA + ti * GPB_NB) + (size_t)rA * ld;
+    J.B = d.Kinv + rA + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.C = d.A + (rA + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(GPB_NB, M - ti * GPB_NB);
+    J.nrem = GPB_NB;
+    J.klo = 0; J.khi = min(M, (ti + 1) * GPB_NB);
+    J.alpha = -1.0; J.beta = 0.0;
+    return true;
+  }
+};
+
+// inv(K) = W^T W, lower tiles only, k >= tile row start (W lower triangular), out of place into Kinv
+struct GeoLauum {
+  const GpbMat* mats;
+  __device__ bool operator()(TileJob& J) const {
+    const GpbMat& d = mats[blockIdx.z];
+    const int T = (d.n + GPB_NB - 1) / GPB_NB;
+    int ti, tj;
+    if (!tri_map(blockIdx.x, T, 0, T, ti, tj)) return false;
+    const size_t ld = d.ld;
+    J.A = d.A + (size_t)(ti * GPB_NB) * ld;
+    J.B = d.A + (size_t)(tj * GPB_NB) * ld;
+    J.C = d.Kinv + ti * GPB_NB + (size_t)(tj * GPB_NB) * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(GPB_NB, d.n - ti * GPB_NB);
+    J.nrem = min(GPB_NB, d.n - tj * GPB_NB);
+    J.klo = ti * GPB_NB; J.khi = d.n;
+    J.alpha = 1.0; J.beta = 0.0;
+    return true;
+  }
+};
+
+struct GeoPlain {
+  const double* A; const double* B; double* C;
+  int lda, ldb, ldc, M, N, K, akm, bkm;
+  double alpha, beta;
+  __device__ bool operator()(TileJob& J) const {
+    const int i0 = blockIdx.x * GPB_NB, j0 = blockIdx.y * GPB_NB;
+    J.A = akm ? A + (size_t)i0 * lda : A + i0;
+    J.B = bkm ? B + (size_t)j0 * ldb : B + j0;
+    J.C = C + i0 + (size_t)j0 * ldc;
+    J.lda = lda; J.ldb = ldb; J.ldc = ldc;
+    J.mrem = min(GPB_NB, M - i0); J.nrem = min(GPB_NB, N - j0);
+    J.klo = 0; J.khi = K; J.alpha = alpha; J.beta = beta;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// diagonal block: Cholesky of a 128 x 128 block in shared memory (+ rows of the carried y^T that fall inside the
+// block), log-det partial, then the block's triangular inverse for the panel product.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int D_LD = 129;
+constexpr int D_SMEM_BYTES = (GPB_NB * D_LD + GPB_NB) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__ mats, int k) {
+  extern __shared__ __align__(16) double dsm[];
+  double* As = dsm;
+  double* vt = dsm + GPB_NB * D_LD;
+  __shared__ int s_info;
+  const GpbMat d = mats[blockIdx.x];
+  const int nrows = d.n + d.aug;
+  const int r0 = k * GPB_NB;
+  if (r0 >= d.n) return;
+  const int bs = min(GPB_NB, nrows - r0);  // rows held by the block (pivot rows + carried rows)
+  const int bf = min(GPB_NB, d.n - r0);    // pivots
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ld = d.ld;
+  double* Ag = d.A + r0 + (size_t)r0 * ld;
+
+  if (tid == 0) s_info = 0;
+  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), j = idx >> 7;
+    double v = 0.0;
+    if (i < bs && j < bs && i >= j) v = Ag[i + (size_t)j * ld];
+    As[i + j * D_LD] = v;
+  }
+  __syncthreads();
+
+  for (int j = 0; j < bf; ++j) {
+    const double ajj = As[j + j * D_LD];
+    if (!(ajj > 0.0) && tid == 0 && s_info == 0) s_info = r0 + j + 1;
+    const double inv = 1.0 / sqrt(ajj);
+    for (int i = j + 1 + tid; i < bs; i += 256) As[i + j * D_LD] *= inv;
+    __syncthreads();
+    for (int c = j + 1 + warp; c < bs; c += 8) {
+      const double lcj = As[c + j * D_LD];
+      for (int i = c + lane; i < bs; i += 32) As[i + c * D_LD] -= As[i + j * D_LD] * lcj;
+    }
+    __syncthreads();
+  }
+  // diagonal: A_jj (fully updated, untouched above) -> L_jj ; log-det partial
+  double lsum = 0.0;
+  if (tid < bf) {
+    const double ljj = sqrt(As[tid + tid * D_LD]);
+    As[tid + tid * D_LD] = ljj;
+    lsum = log(ljj);
+  }
+  if (tid < GPB_NB) vt[tid] = lsum;
+  __syncthreads();
+  if (warp == 0) {
+    double v = vt[lane] + vt[lane + 32] + vt[lane + 64] + vt[lane + 96];
+    v = warp_sum(v);
+    if (lane == 0) {
+      d.part[k] = v;
+      if (s_info != 0 && *d.info == 0) *d.info = s_info;
+    }
+  }
+  // write L back (explicit zeros above the diagonal of the block)
+  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), j = idx >> 7;
+    if (i < bs && j < bs) Ag[i + (size_t)j * ld] = (i >= j) ? As[i + j * D_LD] : 0.0;
+  }
+  __syncthreads();
+
+  // in-place inverse of the bf x bf lower-triangular pivot block (column sweep from the last column)
+  for (int j = bf - 1; j >= 0; --j) {
+    const double wjj = 1.0 / As[j + j * D_LD];
+    for (int i = j + 1 + tid; i < bf; i += 256) vt[i] = As[i + j * D_LD];
+    __syncthreads();
+    for (int i = j + 1 + tid; i < bf; i += 256) {
+      double s = 0.0;
+      for (int kk = j + 1; kk <= i; ++kk) s += As[i + kk * D_LD] * vt[kk];
+      As[i + j * D_LD] = -s * wjj;
+    }
+    if (tid == 0) As[j + j * D_LD] = wjj;
+    __syncthreads();
+  }
+  double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), j = idx >> 7;
+    Wg[idx] = (i >= j && i < bf) ? As[i + j * D_LD] : 0.0;
+  }
+}
+
+// copy the inverted diagonal blocks into place (level 0 of the recursive-doubling inverse)
+__global__ void diag_copy_kernel(const GpbMat* __restrict__ mats) {
+  const GpbMat d = mats[blockIdx.y];
+  const int k = blockIdx.x;
+  const int r0 = k * GPB_NB;
+  if (r0 >= d.n) return;
+  const int bf = min(GPB_NB, d.n - r0);
+  const double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+  double* Ag = d.A + r0 + (size_t)r0 * d.ld;
+  for (int idx = threadIdx.x; idx < GPB_NB * GPB_NB; idx += blockDim.x) {
+    const int i = idx & (GPB_NB - 1), j = idx >> 7;
+    if (i < bf && j < bf) Ag[i + (size_t)j * d.ld] = Wg[idx];
+  }
+}
+
+// nll = 1/2 z^T z + sum log diag L + 1/2 n log(2 pi)   (Metrics/LogLikelihood.py:39-49,65); also gathers z
+__global__ void finalize_kernel(const GpbMat* __restrict__ mats, double log2pi) {
+  const GpbMat d = mats[blockIdx.x];
+  const int n = d.n;
+  const size_t ld = d.ld;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d.zvec[i] = d.A[n + (size_t)i * ld];
+  if (threadIdx.x == 0) {
+    const int nblk = (n + GPB_NB - 1) / GPB_NB;
+    double logdet = 0.0;
+    for (int k = 0; k < nblk; ++k) logdet += d.part[k];
+    const double quad = -d.A[n + (size_t)n * ld];
+    double nll = 0.5 * quad + logdet + 0.5 * ((double)n * log2pi);
+    if (*d.info != 0) nll = nan("");
+    *d.nll = nll;
+  }
+}
+
+// alpha = W^T z : one warp per column of the lower-triangular W
+__global__ void __launch_bounds__(256) alpha_kernel(const GpbMat* __restrict__ mats) {
+  const GpbMat d = mats[blockIdx.y];
+  const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (col >= d.n) return;
+  const int lane = threadIdx.x & 31;
+  const double* w = d.A + (size_t)col * d.ld;
+  double s = 0.0;
+  for (int i = col + lane; i < d.n; i += 32) s += w[i] * d.zvec[i];
+  s = warp_sum(s);
+  if (lane == 0) d.alpha[col] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// standalone blocked triangular solves with the stored diagonal-block inverses (get_L_alpha without gradient)
+//   forward : v = y, for k: x_k = Wd_k v_k ; v[i>blk k] -= L[i, blk k] x_k          (x = zvec)
+//   backward: v = z, for k desc: x_k = Wd_k^T v_k ; v[c<blk k] -= L[blk k, c]^T x_k  (x = alpha)
+// Every CTA recomputes x_k (128 x 128 matvec from L2) so that a step is one launch.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trsv_step_kernel(const GpbMat* __restrict__ mats, int k, int transposed) {
+  __shared__ double xk[GPB_NB];
+  __shared__ double vk[GPB_NB];
+  const GpbMat d = mats[blockIdx.y];
+  const int r0 = k * GPB_NB;
+  if (r0 >= d.n) return;
+  const int bf = min(GPB_NB, d.n - r0);
+  const int tid = threadIdx.x;
+  const double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+  double* v = d.tmpv;
+  double* x = transposed ? d.alpha : d.zvec;
+  if (tid < GPB_NB) vk[tid] = (tid < bf) ? v[r0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < GPB_NB) {
+    double s = 0.0;
+    if (tid < bf) {
+      if (!transposed) { for (int j = 0; j <= tid; ++j) s += Wg[tid + j * GPB_NB] * vk[j]; }
+      else { for (int j = tid; j < bf; ++j) s += Wg[j + tid * GPB_NB] * vk[j]; }
+    }
+    xk[tid] = s;
+    if (blockIdx.x == 0 && tid < bf) x[r0 + tid] = s;
+  }
+  __syncthreads();
+  const size_t ld = d.ld;
+  if (!transposed) {
+    const int i = r0 + GPB_NB + blockIdx.x * 256 + tid;
+    if (i < d.n) {
+      const double* Lr = d.A + i + (size_t)r0 * ld;
+      double s = 0.0;
+      for (int j = 0; j < GPB_NB; ++j) s += Lr[(size_t)j * ld] * xk[j];
+      v[i] -= s;
+    }
+  } else {
+    const int lane = tid & 31;
+    const int c = blockIdx.x * 8 + (tid >> 5);
+    if (c < r0) {
+      const double* Lc = d.A + r0 + (size_t)c * ld;
+      double s = 0.0;
+      for (int j = lane; j < bf; j += 32) s += Lc[j] * xk[j];
+      s = warp_sum(s);
+      if (lane == 0) v[c] -= s;
+    }
+  }
+}
+
+__global__ void trsv_init_kernel(const GpbMat* __restrict__ mats, int transposed) {
+  const GpbMat d = mats[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.n) d.tmpv[i] = transposed ? d.zvec[i] : d.y[i];
+}
+
+__global__ void zero_upper_kernel(double* A, int n, int ld) {
+  const int j = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < j && i < n) A[i + (size_t)j * ld] = 0.0;
+}
+__global__ void symmetrize_kernel(double* A, int n, int ld) {
+  // A[i,j] (i<j) = A[j,i]; 32x32 tiles through shared memory for coalescing on both sides
+  __shared__ double t[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bi > bj) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // read the lower tile (rows bj*32.., cols bi*32..)
+  for (int r = ty; r < 32; r += 8) {
+    const int gi = bj * 32 + tx, gj = bi * 32 + r;
+    t[r][tx] = (gi < n && gj < n) ? A[gi + (size_t)gj * ld] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int gi = bi * 32 + tx, gj = bj * 32 + r;  // upper element (gi < gj)
+    if (gi < n && gj < n && gi < gj) A[gi + (size_t)gj * ld] = t[tx][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------------------------
+#define GPB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+template <bool AKM, bool BKM, class Geo>
+static cudaError_t launch_gemm(const Geo& geo, dim3 grid, cudaStream_t s) {
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  gemm_kernel<AKM, BKM, Geo><<<grid, G_THREADS, G_SMEM_BYTES, s>>>(geo);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+template <bool AKM, bool BKM, class Geo>
+static cudaError_t set_smem() {
+  return cudaFuncSetAttribute(gemm_kernel<AKM, BKM, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+}
+
+cudaError_t linalg_init() {
+  GPB_CK((set_smem<false, false, GeoSyrk>()));
+  GPB_CK((set_smem<false, false, GeoPanel>()));
+  GPB_CK((set_smem<false, true, GeoTrtriT>()));
+  GPB_CK((set_smem<false, true, GeoTrtriW>()));
+  GPB_CK((set_smem<true, true, GeoLauum>()));
+  GPB_CK((set_smem<false, false, GeoPlain>()));
+  GPB_CK((set_smem<false, true, GeoPlain>()));
+  GPB_CK((set_smem<true, false, GeoPlain>()));
+  GPB_CK((set_smem<true, true, GeoPlain>()));
+  GPB_CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
+  return cudaSuccess;
+}
+
+cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
+  const int nrows = n_max + aug;
+  const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
+  const int T_all = (nrows + GPB_NB - 1) / GPB_NB;
+  cudaStream_t ms = ex.main;
+  for (int k = 0; k < nblk; ++k) {
+    diag_kernel<<<B, 256, D_SMEM_BYTES, ms>>>(dm, k);
+    ++g_launches;
+    GPB_CK(cudaGetLastError());
+    const int Tk = T_all - (k + 1);
+    if (Tk <= 0 || (k + 1) * GPB_NB > n_max) continue;
+    GPB_CK((launch_gemm<false, false>(GeoPanel{dm, k}, dim3(Tk, 1, B), ms)));
+    if (!lookahead) {
+      GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 0, Tk}, dim3((unsigned)tri_count(Tk, 0, Tk), 1, B), ms)));
+      continue;
+    }
+    if (k > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(k - 1) & 1], 0));
+    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 0, 1}, dim3((unsigned)tri_count(Tk, 0, 1), 1, B), ms)));
+    GPB_CK(cudaEventRecord(ex.ev_e[k & 1], ms));
+    GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[k & 1], 0));
+    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 1, 2}, dim3((unsigned)tri_count(Tk, 1, 2), 1, B), ex.side)));
+    GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ex.side));
+    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 2, Tk}, dim3((unsigned)tri_count(Tk, 2, Tk), 1, B), ex.side)));
+  }
+  if (lookahead) {
+    GPB_CK(cudaEventRecord(ex.ev_join, ex.side));
+    GPB_CK(cudaStreamWaitEvent(ms, ex.ev_join, 0));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t run_finalize(const GpbMat* dm, int B, double log2pi, cudaStream_t s) {
+  finalize_kernel<<<B, 256, 0, s>>>(dm, log2pi);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t run_trtri(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+  const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
+  diag_copy_kernel<<<dim3(nblk, B), 256, 0, s>>>(dm);
+  ++g_launches;
+  GPB_CK(cudaGetLastError());
+  for (long long sz = GPB_NB; sz < n_max; sz *= 2) {
+    const int ts = (int)(sz / GPB_NB);
+    const int nsub = (int)((n_max + 2 * sz - 1) / (2 * sz));
+    GPB_CK((launch_gemm<false, true>(GeoTrtriT{dm, (int)sz}, dim3(ts * ts, nsub, B), s)));
+    GPB_CK((launch_gemm<false, true>(GeoTrtriW{dm, (int)sz}, dim3(ts * ts, nsub, B), s)));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t run_alpha(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+  alpha_kernel<<<dim3((n_max + 7) / 8, B), 256, 0, s>>>(dm);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t run_lauum(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+  const int T = (n_max + GPB_NB - 1) / GPB_NB;
+  return launch_gemm<true, true>(GeoLauum{dm}, dim3((unsigned)tri_count(T, 0, T), 1, B), s);
+}
+
+cudaError_t run_trsv(const GpbMat* dm, int B, int n_max, int transposed, cudaStream_t s) {
+  const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
+  trsv_init_kernel<<<dim3((n_max + 255) / 256, B), 256, 0, s>>>(dm, transposed);
+  ++g_launches;
+  GPB_CK(cudaGetLastError());
+  if (!transposed) {
+    for (int k = 0; k < nblk; ++k) {
+      const int rest = n_max - (k + 1) * GPB_NB;
+      const int gx = rest > 0 ? (rest + 255) / 256 : 1;
+      trsv_step_kernel<<<dim3(gx, B), 256, 0, s>>>(dm, k, 0);
+      ++g_launches;
+      GPB_CK(cudaGetLastError());
+    }
+  } else {
+    for (int k = nblk - 1; k >= 0; --k) {
+      const int cols = k * GPB_NB;
+      const int gx = cols > 0 ? (cols + 7) / 8 : 1;
+      trsv_step_kernel<<<dim3(gx, B), 256, 0, s>>>(dm, k, 1);
+      ++g_launches;
+      GPB_CK(cudaGetLastError());
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t run_zero_upper(double* A, int n, int ld, cudaStream_t s) {
+  if (n <= 1) return cudaSuccess;
+  zero_upper_kernel<<<dim3((n + 255) / 256, n), 256, 0, s>>>(A, n, ld);
+  ++g_launches;
+  return cudaGetLastError();
+}
+cudaError_t run_symmetrize(double* A, int n, int ld, cudaStream_t s) {
+  const int t = (n + 31) / 32;
+  symmetrize_kernel<<<dim3(t, t), dim3(32, 8), 0, s>>>(A, n, ld);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+// FP64 pipe probes: kind 0 = DMMA.8x8x4 chains, kind 1 = DFMA chains (register operands only)
+__global__ void __launch_bounds__(256) microbench_kernel(int kind, int iters, double* out) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = 0.0;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  if (kind == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmma884(c[2 * i], c[2 * i + 1], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) c[i] = fma(c[i], b, a);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 123.456) out[0] = s;
+}
+cudaError_t run_microbench(int kind, int iters, int blocks, cudaStream_t s) {
+  static double* sink = nullptr;
+  if (!sink) GPB_CK(cudaMalloc(&sink, 64));
+  microbench_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+cudaError_t run_gemm_plain(int akm, int bkm, const double* A, int lda, const double* Bm, int ldb, double* C, int ldc,
+                           int M, int N, int K, double alpha, double beta, cudaStream_t s) {
+  GeoPlain g{A, Bm, C, lda, ldb, ldc, M, N, K, akm, bkm, alpha, beta};
+  dim3 grid((M + GPB_NB - 1) / GPB_NB, (N + GPB_NB - 1) / GPB_NB, 1);
+  if (!akm && !bkm) return launch_gemm<false, false>(g, grid, s);
+  if (!akm && bkm) return launch_gemm<false, true>(g, grid, s);
+  if (akm && !bkm) return launch_gemm<true, false>(g, grid, s);
+  return launch_gemm<true, true>(g, grid, s);
+}
+
+}  // namespace gpb

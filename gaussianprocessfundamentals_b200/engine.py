@@ -1,0 +1,209 @@
+"""Host-side driver of libgpb: device programs, plans (workspace + launch sequence) and their torch views.
+
+PyTorch is used for plumbing only (device memory, streams, CUDA graphs); every FLOP of the path runs in libgpb's
+kernels.  There is no CPU fallback: constructing a DeviceProgram or a Plan without CUDA raises.
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .program import CompiledProgram, compile_spec, flatten_hp, unflatten_grad
+
+STAGE_ASSEMBLE, STAGE_POTRF, STAGE_NLL, STAGE_INVERSE, STAGE_GRAD, STAGE_BACKSOLVE = 1, 2, 4, 8, 16, 32
+STAGES_LML, STAGES_LML_GRAD = 7, 31
+BUF_A, BUF_KINV, BUF_ALPHA, BUF_Z, BUF_X, BUF_Y, BUF_HP, BUF_NOISE, BUF_NLL, BUF_GRAD, BUF_INFO = range(11)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.GpbError("gaussianprocessfundamentals_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NotPositiveDefinite(ArithmeticError):
+    """Cholesky met a non-positive pivot (the reference surfaces TF's InvalidArgumentError here)."""
+
+    def __init__(self, info):
+        super().__init__("Cholesky decomposition was not successful: non-positive pivot at index %s (1-based)" % (info,))
+        self.info = info
+
+
+class DeviceProgram:
+    """A compiled kernel tree resident on the device (gpb_program_t)."""
+
+    _cache = {}
+
+    def __init__(self, compiled: CompiledProgram, cp_mode: int):
+        require_cuda()
+        lib = _lib.load()
+        self.compiled = compiled
+        self.cp_mode = int(cp_mode)
+        code = np.ascontiguousarray(compiled.code, dtype=np.int32)
+        h = ctypes.c_void_p()
+        _lib.check(lib.gpb_program_create(code.ctypes.data_as(_lib.c_int32_p), compiled.n_ops, compiled.dim,
+                                          self.cp_mode, ctypes.byref(h)), "gpb_program_create")
+        self.handle = h
+        assert lib.gpb_program_num_hp(h) == compiled.n_hp
+
+    @classmethod
+    def get(cls, spec, dim: int, scaled: bool, cp_mode: int) -> "DeviceProgram":
+        compiled = compile_spec(spec, dim, scaled)
+        key = (compiled.signature(), int(cp_mode), torch.cuda.current_device())
+        prog = cls._cache.get(key)
+        if prog is None:
+            prog = cls(compiled, cp_mode)
+            cls._cache[key] = prog
+        return prog
+
+    @property
+    def n_hp(self) -> int:
+        return self.compiled.n_hp
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and _lib._lib is not None:
+                _lib._lib.gpb_program_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def assemble(prog: DeviceProgram, X: torch.Tensor, X2: Optional[torch.Tensor], hp_flat: torch.Tensor,
+             noise: Optional[torch.Tensor], lower_only: bool = False) -> torch.Tensor:
+    """K[n, m] (logical, row-major semantics) as a transposed view of the column-major buffer the kernel writes."""
+    require_cuda()
+    lib = _lib.load()
+    n = X.shape[0]
+    m = n if X2 is None else X2.shape[0]
+    ld = max(n, 1)
+    buf = torch.empty((m, ld), dtype=torch.float64, device=X.device)
+    if lower_only:
+        buf.zero_()
+    _lib.check(lib.gpb_assemble(prog.handle, X.data_ptr(), None if X2 is None else X2.data_ptr(), n, m,
+                                hp_flat.data_ptr() if hp_flat.numel() else None,
+                                None if noise is None else noise.data_ptr(), buf.data_ptr(), ld,
+                                1 if lower_only else 0, _stream_ptr()), "gpb_assemble")
+    return buf.t()[:n, :m]
+
+
+class Plan:
+    """B independent GPs evaluated together: assembly -> Cholesky (+ carried y) -> NLL -> inverse -> gradient."""
+
+    def __init__(self, programs: Sequence[DeviceProgram], ns: Sequence[int], want_grad: bool = True,
+                 device: Optional[torch.device] = None):
+        require_cuda()
+        lib = _lib.load()
+        self.lib = lib
+        self.programs = list(programs)
+        self.ns = [int(v) for v in ns]
+        self.B = len(self.programs)
+        assert self.B == len(self.ns) and self.B > 0
+        self.want_grad = bool(want_grad)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        handles = (ctypes.c_void_p * self.B)(*[p.handle for p in self.programs])
+        n_arr = (ctypes.c_int64 * self.B)(*self.ns)
+        h = ctypes.c_void_p()
+        _lib.check(lib.gpb_plan_create(self.B, handles, n_arr, 1 if want_grad else 0, ctypes.byref(h)), "gpb_plan_create")
+        self.handle = h
+        self.ws_bytes = int(lib.gpb_plan_workspace_bytes(h))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.gpb_plan_bind(h, ctypes.c_void_p(self.ws.data_ptr())), "gpb_plan_bind")
+        self.hp_sizes = [p.n_hp for p in self.programs]
+        self.grad_offsets = np.concatenate([[0], np.cumsum([s + 1 for s in self.hp_sizes])]).astype(np.int64)
+        # host staging for eval_host
+        self._nll_h = np.zeros(self.B, dtype=np.float64)
+        self._grad_h = np.zeros(int(self.grad_offsets[-1]), dtype=np.float64)
+        self._info_h = np.zeros(self.B, dtype=np.int32)
+
+    # -- buffers -----------------------------------------------------------------------------------------------
+    def buffer(self, b: int, which: int) -> torch.Tensor:
+        ptr, nbytes, ld = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int64()
+        _lib.check(self.lib.gpb_plan_buffer(self.handle, b, which, ctypes.byref(ptr), ctypes.byref(nbytes),
+                                            ctypes.byref(ld)), "gpb_plan_buffer")
+        off = ptr.value - self.ws.data_ptr()
+        raw = self.ws[off:off + nbytes.value]
+        if which == BUF_INFO:
+            return raw.view(torch.int32)
+        t = raw.view(torch.float64)
+        n = self.ns[b]
+        if which == BUF_A:
+            return t.view(n + 1, ld.value)       # row r of this view = column r of the column-major matrix
+        if which == BUF_KINV:
+            return t.view(n, ld.value)
+        if which == BUF_X:
+            return t.view(n, -1)
+        return t
+
+    def lower_matrix(self, b: int, which: int = BUF_A) -> torch.Tensor:
+        """logical n x n matrix view M[i, j] (lower triangle valid) of BUF_A / BUF_KINV"""
+        n = self.ns[b]
+        return self.buffer(b, which)[:n, :n].t()
+
+    def set_data(self, b: int, X: torch.Tensor, y: torch.Tensor):
+        self.buffer(b, BUF_X).copy_(X.reshape(self.ns[b], -1).to(self.device, torch.float64))
+        self.buffer(b, BUF_Y).copy_(y.reshape(-1).to(self.device, torch.float64))
+
+    def set_hp(self, b: int, hp_flat, noise: float):
+        if self.hp_sizes[b]:
+            self.buffer(b, BUF_HP).copy_(torch.as_tensor(np.asarray(hp_flat, dtype=np.float64)))
+        self.buffer(b, BUF_NOISE).copy_(torch.as_tensor(np.asarray([noise], dtype=np.float64)))
+
+    # -- evaluation --------------------------------------------------------------------------------------------
+    def eval(self, stages: int = STAGES_LML_GRAD):
+        _lib.check(self.lib.gpb_plan_eval(self.handle, int(stages), _stream_ptr()), "gpb_plan_eval")
+
+    def results(self):
+        """(nll[B], [grad_b], info[B]) read back from the device (synchronises)."""
+        nll = torch.stack([self.buffer(b, BUF_NLL)[0] for b in range(self.B)]).cpu().numpy()
+        info = torch.stack([self.buffer(b, BUF_INFO)[0] for b in range(self.B)]).cpu().numpy()
+        grads = [self.buffer(b, BUF_GRAD).cpu().numpy().copy() for b in range(self.B)]
+        return nll, grads, info
+
+    def eval_host(self, hp_flats: Sequence[np.ndarray], noises: Sequence[float], Xs=None, ys=None,
+                  stages: int = STAGES_LML_GRAD):
+        """The end-to-end call: host buffers in, host results out (H2D + kernels + D2H + sync inside)."""
+        B = self.B
+        keep = []
+
+        def ptr_array(arrs):
+            if arrs is None:
+                return None
+            out = (ctypes.c_void_p * B)()
+            for b in range(B):
+                a = np.ascontiguousarray(arrs[b], dtype=np.float64)
+                keep.append(a)
+                out[b] = a.ctypes.data
+            return out
+
+        hp_ptrs = ptr_array([np.zeros(1) if len(h) == 0 else h for h in hp_flats])
+        x_ptrs = ptr_array(Xs)
+        y_ptrs = ptr_array(ys)
+        nz = np.ascontiguousarray(noises, dtype=np.float64)
+        _lib.check(self.lib.gpb_plan_eval_host(self.handle, int(stages), x_ptrs, y_ptrs, hp_ptrs,
+                                               nz.ctypes.data, self._nll_h.ctypes.data, self._grad_h.ctypes.data,
+                                               self._info_h.ctypes.data, _stream_ptr()), "gpb_plan_eval_host")
+        grads = [self._grad_h[self.grad_offsets[b]:self.grad_offsets[b + 1]].copy() for b in range(B)]
+        return self._nll_h.copy(), grads, self._info_h.copy()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and _lib._lib is not None:
+                _lib._lib.gpb_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def gemm(a_kmajor: bool, b_kmajor: bool, A: torch.Tensor, lda: int, Bm: torch.Tensor, ldb: int, C: torch.Tensor,
+         ldc: int, M: int, N: int, K: int, alpha: float, beta: float):
+    lib = _lib.load()
+    _lib.check(lib.gpb_gemm(int(a_kmajor), int(b_kmajor), A.data_ptr(), lda, Bm.data_ptr(), ldb, C.data_ptr(), ldc,
+                            M, N, K, float(alpha), float(beta), _stream_ptr()), "gpb_gemm")
+
+
+def launch_count() -> int:
+    return int(_lib.load().gpb_launch_count())

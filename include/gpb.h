@@ -1,0 +1,124 @@
+/* libgpb - C-ABI of the B200-native exact-GP likelihood path (drop-in arithmetic for gpbasics 2.0.0).
+ *
+ * The reference (Bernsai/GaussianProcessFundamentals) has no FFI: its hot path is Python calling TensorFlow.  Every
+ * entry point below therefore cites the reference *Python* interface whose arithmetic it replaces
+ * (paths relative to main/gpbasics/).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; all matrices FP64; device pointers unless the name ends in _host
+ *   - matrices are column-major with a leading dimension (a row-major [n,m] tensor is the same memory as the
+ *     column-major m x n transpose; symmetric / triangular results are exposed through transposed views)
+ *   - `stream` is a cudaStream_t passed as void*; compute calls are asynchronous on it and never allocate
+ *   - return 0 on success, -k if argument k (1-based) is invalid, 1000 + cudaError_t on a CUDA failure;
+ *     gpb_last_error() returns a description.  Non positive-definite matrices are reported through `info`
+ *     (LAPACK convention: 1-based index of the first non-positive pivot), not through the return code.
+ */
+#ifndef GPB_H_
+#define GPB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb_program gpb_program_t;
+typedef struct gpb_plan gpb_plan_t;
+
+/* op codes of the postfix kernel program, 4 int32 words per op {op, a, b, c}; see csrc/program.cuh */
+#define GPB_SE 1
+#define GPB_PER 2
+#define GPB_LIN 3
+#define GPB_MAT32 4
+#define GPB_MAT52 5
+#define GPB_WN 6
+#define GPB_SE_ARD 7
+#define GPB_ADD2 16
+#define GPB_MUL2 17
+#define GPB_CPW 18
+
+/* gpb_plan_eval stage bits */
+#define GPB_STAGE_ASSEMBLE 1   /* K + s2 I (+ y as carried row)          */
+#define GPB_STAGE_POTRF 2      /* L, z = L^-1 y, log det                  */
+#define GPB_STAGE_NLL 4        /* negative log marginal likelihood        */
+#define GPB_STAGE_INVERSE 8    /* W = L^-1, alpha = W^T z, Kinv = W^T W  */
+#define GPB_STAGE_GRAD 16      /* d nll / d theta, d nll / d s2           */
+#define GPB_STAGE_BACKSOLVE 32 /* alpha by substitution, L left intact    */
+#define GPB_STAGES_LML 7
+#define GPB_STAGES_LML_GRAD 31
+
+/* buffers of a plan that can be mapped by the host language (gpb_plan_buffer) */
+#define GPB_BUF_A 0      /* (n+1) columns x ld: K+s2I -> L -> L^-1, lower; row n carries y^T -> z^T */
+#define GPB_BUF_KINV 1   /* n columns x ld: K^-1, lower                                              */
+#define GPB_BUF_ALPHA 2  /* [n]                                                                      */
+#define GPB_BUF_Z 3      /* [n]                                                                      */
+#define GPB_BUF_X 4      /* [n x dim] row-major                                                      */
+#define GPB_BUF_Y 5      /* [n]                                                                      */
+#define GPB_BUF_HP 6     /* [n_hp]                                                                   */
+#define GPB_BUF_NOISE 7  /* [1]                                                                      */
+#define GPB_BUF_NLL 8    /* [1]                                                                      */
+#define GPB_BUF_GRAD 9   /* [n_hp + 1], last = d nll / d s2                                          */
+#define GPB_BUF_INFO 10  /* [1] int32                                                                */
+
+int gpb_version(void);
+const char* gpb_last_error(void);
+/* Number of CUDA kernels launched by this library since load (bench.py's gpu_launches). */
+long long gpb_launch_count(void);
+
+/* ---- kernel programs --------------------------------------------------------------------------------------
+ * A compiled kernel tree.  Replaces the recursive Kernel.get_tf_tensor walk
+ * (KernelBasics/Kernel.py:51, BaseKernels.py:114-134,277-294,440-457, Operators.py:207-225,306-326,442-476).
+ * cp_mode: 0 sigmoid, 1 indicator, 2 approx-indicator (global_parameters.py:10-13,44).                       */
+int gpb_program_create(const int32_t* code, int n_ops, int dim, int cp_mode, gpb_program_t** out);
+int gpb_program_num_hp(const gpb_program_t* prog);
+void gpb_program_destroy(gpb_program_t* prog);
+
+/* ---- covariance assembly ----------------------------------------------------------------------------------
+ * K[i + j*ldk] = k(X[i,:], X2[j,:]) (+ noise on the diagonal when X2 == NULL).  X: [n x dim] row-major, X2: [m x dim]
+ * row-major or NULL for the symmetric case; hp, noise: device.  lower_only != 0 writes i >= j only.
+ * Replaces HolisticCovarianceMatrix.get_K / get_K_noised / get_K_s / get_K_ss
+ * (Statistics/CovarianceMatrix.py:187-206,213-221,277-286).                                                    */
+int gpb_assemble(const gpb_program_t* prog, const double* X, const double* X2, int64_t n, int64_t m,
+                 const double* hp, const double* noise, double* K, int64_t ldk, int lower_only, void* stream);
+
+/* ---- plans: the fused LML (+ gradient) evaluation over a batch of independent GPs --------------------------
+ * One plan = B GPs (B = 1: GaussianProcess; B > 1: the blocks of a Blockwise/PartitionedGaussianProcess, or a
+ * batch of candidate kernels).  Replaces LogLikelihood.get_metric (Metrics/LogLikelihood.py:30-65) with
+ * Metric.get_alpha_cholesky / get_log_determinant_cholesky (Metrics/Metrics.py:138-139,152-154),
+ * HolisticCovarianceMatrix.get_L_K / get_L_alpha (Statistics/CovarianceMatrix.py:247-265),
+ * SegmentedCovarianceMatrix.get_*_blocks (:316-339,:469-506), BlockwiseLogLikelihood.get_metric
+ * (Metrics/LogLikelihood.py:77-104, per-block values; the caller sums) and the GradientTape gradient of
+ * Optimizer/Fitter.py:124-132,154-158.                                                                         */
+int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb_plan_t** out);
+size_t gpb_plan_workspace_bytes(const gpb_plan_t* plan);
+/* workspace: device memory of gpb_plan_workspace_bytes() bytes, 256-byte aligned, owned by the caller. */
+int gpb_plan_bind(gpb_plan_t* plan, void* workspace);
+/* device address / byte size of one of the plan's buffers for GP b (all live inside the workspace) */
+int gpb_plan_buffer(const gpb_plan_t* plan, int b, int which, void** ptr, size_t* bytes, int64_t* ld);
+/* asynchronous, graph-capturable: inputs are read from the GPB_BUF_X/Y/HP/NOISE buffers */
+int gpb_plan_eval(gpb_plan_t* plan, int stages, void* stream);
+/* host-buffer call (the end-to-end path): copies X, y, hp, noise of every GP to the device, evaluates, copies
+ * nll[B], grad (concatenated, n_hp_b + 1 each) and info[B] back and synchronises the stream.
+ * X_host / y_host may be NULL to keep the inputs of the previous call resident.                               */
+int gpb_plan_eval_host(gpb_plan_t* plan, int stages, const double* const* X_host, const double* const* y_host,
+                       const double* const* hp_host, const double* noise_host, double* nll_host, double* grad_host,
+                       int* info_host, void* stream);
+void gpb_plan_destroy(gpb_plan_t* plan);
+
+/* ---- utilities used by the host mirror and the tests --------------------------------------------------------- */
+/* C = alpha * op(A) op(B)^T + beta C on the FP64 tensor-core mainloop (a_kmajor: element (i,k) at A[k + i*lda]) */
+int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+             int M, int N, int K, double alpha, double beta, void* stream);
+int gpb_zero_upper(double* A, int n, int ld, void* stream);   /* zero the strict upper triangle (column-major) */
+int gpb_symmetrize(double* A, int n, int ld, void* stream);   /* copy the lower triangle into the upper one    */
+
+/* FP64 pipe probe used by bench.py to measure the roofline denominator: kind 0 = DMMA.8x8x4 (512 flop per warp
+ * instruction), kind 1 = DFMA (64 flop per warp instruction); every thread issues 8 (kind 0) / 16 (kind 1)
+ * independent instructions per iteration; `blocks` CTAs of 256 threads.                                         */
+int gpb_microbench(int kind, int iters, int blocks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB_H_ */

@@ -1,0 +1,279 @@
+"""GPU parity tests of the CUDA path (through the C-ABI) against the CPU oracle.  Tolerances (north_star):
+relative <= 1e-10 on the log-likelihood, <= 1e-8 on gradients; matrices element-wise to a few ulp."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-10
+GRAD_RTOL = 1e-8
+
+
+def _eng():
+    from gaussianprocessfundamentals_b200 import engine
+    return engine
+
+
+def _data(n, d=1, seed=0, kind="grid"):
+    rng = np.random.default_rng(seed)
+    if d == 1 and kind == "grid":
+        x = np.linspace(0.0, 1.0, n)[:, None]
+    else:
+        x = np.sort(rng.uniform(0, 1, size=(n, d)), axis=0)
+    y = np.sin(12 * x[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    return x, y
+
+
+COMPOSITE = ("MUL", [("ADD", [("SE",), ("PER",)]), ("LIN",)])
+TREES = {
+    "se": (("SE",), [0.1]),
+    "per": (("PER",), [0.5, 0.3]),
+    "lin": (("LIN",), [[0.01]]),
+    "composite": (COMPOSITE, [0.1, 0.1, 0.1, [0.01]]),
+    "mat": (("ADD", [("MAT32",), ("MAT52",), ("WN",)]), [0.2, 0.3]),
+    "deep": (("ADD", [("MUL", [("SE",), ("PER",), ("LIN",)]), ("MUL", [("SE",), ("ADD", [("LIN",), ("PER",)])])]),
+             [0.2, 0.4, 0.25, [0.3], 0.15, [-0.2], 0.6, 0.35]),
+    "cp": (("CP", [("SE",), ("PER",), ("ADD", [("SE",), ("LIN",)])]), [0.31, 0.67, 0.1, 0.2, 0.15, 0.08, [0.5]]),
+}
+
+
+def _flat(entries_hp):
+    out = []
+    for h in entries_hp:
+        out.extend(np.asarray(h, dtype=np.float64).reshape(-1).tolist())
+    return np.asarray(out, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("akm,bkm", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 128, 128), (300, 200, 150), (257, 129, 151), (64, 1, 16), (1, 5, 7)])
+def test_gemm_dmma(akm, bkm, shape):
+    eng = _eng()
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K))
+    Bm = rng.standard_normal((N, K))
+    C0 = rng.standard_normal((M, N))
+    ev = lambda v: v + (v & 1)
+    # column-major storage: an MN-major operand stores (mn, k) at [mn + k*ld]; a K-major one at [k + mn*ld]
+    lda = ev(K + 2) if akm else ev(M + 4)
+    ldb = ev(K + 2) if bkm else ev(N + 6)
+    ldc = M + 3
+    Ah = np.zeros((lda * (M if akm else K),))
+    Bh = np.zeros((ldb * (N if bkm else K),))
+    Ch = np.zeros((ldc * N,))
+    for i in range(M):
+        for k in range(K):
+            Ah[(k + i * lda) if akm else (i + k * lda)] = A[i, k]
+    for j in range(N):
+        for k in range(K):
+            Bh[(k + j * ldb) if bkm else (j + k * ldb)] = Bm[j, k]
+    for i in range(M):
+        Ch[i + np.arange(N) * ldc] = C0[i, :]
+    dev = torch.device("cuda")
+    At, Bt, Ct = (torch.tensor(v, dtype=torch.float64, device=dev) for v in (Ah, Bh, Ch))
+    eng.gemm(akm, bkm, At, lda, Bt, ldb, Ct, ldc, M, N, K, -0.75, 0.5)
+    got = Ct.cpu().numpy()
+    want = -0.75 * A @ Bm.T + 0.5 * C0
+    res = np.array([[got[i + j * ldc] for j in range(N)] for i in range(M)])
+    assert np.max(np.abs(res - want)) <= 1e-12 * max(1.0, np.max(np.abs(want))) * K
+    # beta == 0 must ignore NaNs in C
+    Ct2 = torch.full_like(Ct, float("nan"))
+    eng.gemm(akm, bkm, At, lda, Bt, ldb, Ct2, ldc, M, N, K, 1.0, 0.0)
+    got2 = Ct2.cpu().numpy()
+    res2 = np.array([[got2[i + j * ldc] for j in range(N)] for i in range(M)])
+    assert np.max(np.abs(res2 - A @ Bm.T)) <= 1e-12 * K * max(1.0, np.max(np.abs(A @ Bm.T)))
+
+
+@pytest.mark.parametrize("name", list(TREES))
+@pytest.mark.parametrize("n,m", [(200, 200), (130, 75)])
+def test_assemble_matches_oracle(name, n, m):
+    eng = _eng()
+    tree, hp = TREES[name]
+    x, _ = _data(n)
+    x2 = np.linspace(-0.2, 1.3, m)[:, None] if m != n else x
+    prog = eng.DeviceProgram.get(tree, 1, False, 1)
+    dev = torch.device("cuda")
+    X = torch.tensor(x, device=dev)
+    X2 = None if m == n else torch.tensor(x2, device=dev)
+    hpf = torch.tensor(_flat(hp), device=dev)
+    noise = torch.tensor([0.01], dtype=torch.float64, device=dev)
+    K = eng.assemble(prog, X, X2, hpf, noise if m == n else None).cpu().numpy()
+    hp_t = [torch.tensor(np.asarray(h, dtype=np.float64)) for h in hp]
+    Kref = orc.kernel_matrix(tree, hp_t, torch.tensor(x), torch.tensor(x2), reference_distance=False).numpy()
+    if m == n:
+        Kref = Kref + 0.01 * np.eye(n)
+    scale = max(1.0, np.max(np.abs(Kref)))
+    assert K.shape == Kref.shape
+    assert np.max(np.abs(K - Kref)) <= 5e-15 * scale
+
+
+def _run_plan(eng, tree, hp, n, noise=1e-2, d=1, scaled=False, cp_mode=1, seed=0, want_grad=True, host=False, x=None,
+              y=None):
+    if x is None:
+        x, y = _data(n, d, seed)
+    prog = eng.DeviceProgram.get(tree, d, scaled, cp_mode)
+    plan = eng.Plan([prog], [n], want_grad=want_grad)
+    hpf = _flat(hp)
+    if host:
+        nll, grads, info = plan.eval_host([hpf], [noise], [x], [y.reshape(-1)],
+                                          stages=eng.STAGES_LML_GRAD if want_grad else eng.STAGES_LML)
+    else:
+        plan.set_data(0, torch.tensor(x), torch.tensor(y))
+        plan.set_hp(0, hpf, noise)
+        plan.eval(eng.STAGES_LML_GRAD if want_grad else eng.STAGES_LML)
+        nll, grads, info = plan.results()
+    return plan, x, y, nll, grads, info
+
+
+@pytest.mark.parametrize("name", ["se", "composite", "deep", "cp", "mat"])
+@pytest.mark.parametrize("n", [64, 128, 129, 300, 1000, 1025])
+def test_nll_and_grad_match_oracle(name, n):
+    eng = _eng()
+    tree, hp = TREES[name]
+    plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, n, host=(n % 2 == 0))
+    assert info[0] == 0
+    ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, reference_distance=False)
+    assert abs(nll[0] - ref) <= LL_RTOL * abs(ref), (nll[0], ref)
+    gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+    got = grads[0]
+    for k in range(len(gflat)):
+        assert abs(got[k] - gflat[k]) <= GRAD_RTOL * max(abs(gflat[k]), 1e-3 * np.max(np.abs(gflat))), (k, got, gflat)
+
+
+def test_factor_buffers_match_lapack():
+    eng = _eng()
+    tree, hp = TREES["composite"]
+    n = 700
+    plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, n, want_grad=False)
+    hp_t = [torch.tensor(np.asarray(h, dtype=np.float64)) for h in hp]
+    _, K, L, alpha = orc.nll(tree, hp_t, torch.tensor(1e-2, dtype=torch.float64), torch.tensor(x), torch.tensor(y),
+                             reference_distance=False, return_parts=True)
+    Lg = torch.tril(plan.lower_matrix(0, eng.BUF_A)).cpu().numpy()
+    assert np.max(np.abs(Lg - L.numpy())) <= 1e-10 * np.max(np.abs(L.numpy()))
+    # standalone back substitution -> alpha
+    plan.eval(eng.STAGE_BACKSOLVE)
+    a = plan.buffer(0, eng.BUF_ALPHA).cpu().numpy()
+    assert np.max(np.abs(a - alpha.numpy().reshape(-1))) <= 1e-8 * np.max(np.abs(alpha.numpy()))
+
+
+def test_inverse_buffers():
+    eng = _eng()
+    tree, hp = TREES["se"]
+    n = 900
+    plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, n)
+    hp_t = [torch.tensor(np.asarray(h, dtype=np.float64)) for h in hp]
+    _, K, L, alpha = orc.nll(tree, hp_t, torch.tensor(1e-2, dtype=torch.float64), torch.tensor(x), torch.tensor(y),
+                             reference_distance=False, return_parts=True)
+    Kn = K.numpy() + 1e-2 * np.eye(n)
+    Kinv = np.linalg.inv(Kn)
+    got = torch.tril(plan.lower_matrix(0, eng.BUF_KINV)).cpu().numpy()
+    assert np.max(np.abs(got - np.tril(Kinv))) <= 1e-9 * np.max(np.abs(Kinv))
+    a = plan.buffer(0, eng.BUF_ALPHA).cpu().numpy()
+    assert np.max(np.abs(a - alpha.numpy().reshape(-1))) <= 1e-9 * np.max(np.abs(alpha.numpy()))
+
+
+def test_scaled_and_smooth_changepoint_gradients():
+    eng = _eng()
+    n = 400
+    x, y = _data(n)
+    # scaled base kernels (p_scaled_base_kernel): every leaf gains sg
+    tree = ("ADD", [("SE",), ("MUL", [("PER",), ("LIN",)])])
+    hp = [0.2, 0.7, 0.3, 0.25, 1.3, [0.1], 0.4]
+    plan, _, _, nll, grads, info = _run_plan(eng, tree, hp, n, scaled=True, x=x, y=y)
+    ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, scaled=True, reference_distance=False)
+    assert abs(nll[0] - ref) <= LL_RTOL * abs(ref)
+    gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+    assert np.max(np.abs(grads[0] - gflat)) <= GRAD_RTOL * np.max(np.abs(gflat))
+    # approx-indicator change points carry gradients (Operators.py:379-385)
+    tree, hp = TREES["cp"]
+    plan, _, _, nll, grads, info = _run_plan(eng, tree, hp, n, cp_mode=2, x=x, y=y)
+    ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, cp_mode=2, reference_distance=False)
+    assert abs(nll[0] - ref) <= LL_RTOL * abs(ref)
+    gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+    assert np.max(np.abs(grads[0] - gflat)) <= GRAD_RTOL * np.max(np.abs(gflat))
+
+
+def test_multidim_and_ard():
+    eng = _eng()
+    n, d = 500, 3
+    rng = np.random.default_rng(4)
+    x = rng.uniform(0, 1, size=(n, d))
+    y = np.sum(np.sin(3 * x), axis=1, keepdims=True) + 0.1 * rng.standard_normal((n, 1))
+    tree = ("ADD", [("SE_ARD",), ("LIN",), ("SE",)])
+    hp = [[0.3, 0.5, 0.8], [0.1, -0.2, 0.3], 0.4]
+    plan, _, _, nll, grads, info = _run_plan(eng, tree, hp, n, d=d, x=x, y=y)
+    ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, reference_distance=False)
+    assert abs(nll[0] - ref) <= LL_RTOL * abs(ref)
+    gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+    assert np.max(np.abs(grads[0] - gflat)) <= GRAD_RTOL * np.max(np.abs(gflat))
+
+
+def test_ragged_batch_matches_singletons():
+    eng = _eng()
+    names = ["se", "composite", "deep", "per", "cp"]
+    ns = [257, 128, 640, 33, 300]
+    progs, xs, ys, hps = [], [], [], []
+    for k, (nm, n) in enumerate(zip(names, ns)):
+        tree, hp = TREES[nm]
+        x, y = _data(n, seed=k)
+        progs.append(eng.DeviceProgram.get(tree, 1, False, 1))
+        xs.append(x); ys.append(y.reshape(-1)); hps.append(_flat(hp))
+    plan = eng.Plan(progs, ns, want_grad=True)
+    nll, grads, info = plan.eval_host(hps, [1e-2] * len(ns), xs, ys)
+    assert np.all(info == 0)
+    for k, (nm, n) in enumerate(zip(names, ns)):
+        tree, hp = TREES[nm]
+        ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, xs[k], ys[k].reshape(-1, 1), reference_distance=False)
+        assert abs(nll[k] - ref) <= LL_RTOL * abs(ref), (nm, nll[k], ref)
+        gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+        assert np.max(np.abs(grads[k] - gflat)) <= GRAD_RTOL * np.max(np.abs(gflat)), nm
+
+
+def test_not_positive_definite_reports_info():
+    eng = _eng()
+    n = 256
+    x = np.zeros((n, 1))  # identical inputs, zero noise -> singular
+    y = np.ones((n, 1))
+    plan, _, _, nll, grads, info = _run_plan(eng, ("SE",), [0.1], n, noise=0.0, x=x, y=y)
+    assert info[0] > 0 and math.isnan(nll[0])
+
+
+def test_known_answer_identity_kernel():
+    """WN kernel: K = (1 + s2) I  ->  closed-form NLL"""
+    eng = _eng()
+    n = 513
+    x, y = _data(n)
+    plan, _, _, nll, grads, info = _run_plan(eng, ("WN",), [], n, noise=0.5, x=x, y=y)
+    want = 0.5 * float(y.T @ y) / 1.5 + 0.5 * n * math.log(1.5) + 0.5 * n * math.log(2 * math.pi)
+    assert abs(nll[0] - want) <= 1e-12 * abs(want)
+
+
+def test_large_roundtrip_properties():
+    """n = 4096 (beyond the look-ahead threshold): L L^T == K + s2 I and Kinv (K + s2 I) == I on random probes."""
+    eng = _eng()
+    tree, hp = TREES["composite"]
+    n = 4096
+    x, y = _data(n)
+    prog = eng.DeviceProgram.get(tree, 1, False, 1)
+    plan = eng.Plan([prog], [n], want_grad=True)
+    plan.set_data(0, torch.tensor(x), torch.tensor(y))
+    plan.set_hp(0, _flat(hp), 1e-2)
+    dev = torch.device("cuda")
+    Kfull = eng.assemble(prog, torch.tensor(x, device=dev), None, torch.tensor(_flat(hp), device=dev),
+                         torch.tensor([1e-2], dtype=torch.float64, device=dev))
+    plan.eval(eng.STAGES_LML)
+    L = torch.tril(plan.lower_matrix(0, eng.BUF_A))
+    v = torch.randn(n, 8, dtype=torch.float64, device=dev)
+    r1 = L @ (L.t() @ v) - Kfull @ v
+    assert float(r1.abs().max()) <= 1e-9 * float((Kfull @ v).abs().max())
+    plan.eval(eng.STAGE_INVERSE)
+    Kl = torch.tril(plan.lower_matrix(0, eng.BUF_KINV))
+    Kinv = Kl + torch.tril(Kl, -1).t()
+    r2 = Kinv @ (Kfull @ v) - v
+    assert float(r2.abs().max()) <= 1e-6 * float(v.abs().max())
