@@ -81,7 +81,7 @@ int gpb_program_create(const int32_t* code, int n_ops, int dim, int cp_mode, gpb
   for (int pc = 0; pc < n_ops; ++pc) {
     const int32_t* w = code + pc * GPB_OP_WORDS;
     const int op = w[0];
-    if (op >= GPB_OP_SE && op <= GPB_OP_SE_ARD) {
+    if (op >= GPB_OP_SE && op <= GPB_OP_L1) {
       const int nq = gpb_leaf_nhp(op, w[2], dim);
       if (w[1] < 0) return fail_arg(1, "negative hyper-parameter offset");
       if (w[1] + nq > n_hp) n_hp = w[1] + nq;
@@ -207,12 +207,16 @@ int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, 
   cudaError_t e = cudaMallocHost(&p->h_in, p->in_bytes + 16);
   if (e == cudaSuccess) e = cudaMallocHost(&p->h_out, p->out_bytes + 16);
   p->own_streams = false;
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->ex.side, cudaStreamNonBlocking);
+  int prio_lo = 0, prio_hi = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.crit, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.side, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&p->ex.ev_e[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_g[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   }
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete p; return fail_cuda(e, "gpb_plan_create"); }
   p->own_streams = true;
   *out = p;
@@ -329,9 +333,12 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
 void gpb_plan_destroy(gpb_plan_t* p) {
   if (!p) return;
   if (p->own_streams) {
+    cudaStreamDestroy(p->ex.crit);
     cudaStreamDestroy(p->ex.side);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); }
-    cudaEventDestroy(p->ex.ev_join);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_join[i]);
+    }
+    cudaEventDestroy(p->ex.ev_fork);
   }
   if (p->h_in) cudaFreeHost(p->h_in);
   if (p->h_out) cudaFreeHost(p->h_out);

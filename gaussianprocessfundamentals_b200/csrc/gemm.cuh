@@ -76,6 +76,19 @@ __device__ __forceinline__ void gemm_tile(const TileJob& J) {
 
   const int nk = (J.khi > J.klo) ? (J.khi - J.klo + G_BK - 1) / G_BK : 0;
 
+  if (J.beta != 0.0) {
+    // the accumulate-into tile is needed only by the epilogue: pull it into L2 now (128 columns x 8 lines)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 256 * q;
+      const int col = idx >> 3, seg = (idx & 7) * 16;
+      if (col < J.nrem && seg < J.mrem) {
+        const double* pp = J.C + (size_t)col * J.ldc + seg;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+      }
+    }
+  }
+
 #pragma unroll
   for (int s = 0; s < G_STAGES - 1; ++s) {
     if (s < nk) {
@@ -122,26 +135,46 @@ __device__ __forceinline__ void gemm_tile(const TileJob& J) {
   }
   cp_async_wait<0>();
 
-  // epilogue: each quad-row of 8 lanes covers 8 consecutive rows (64 B) of one column
+  // epilogue: each quad-row of 8 lanes covers 8 consecutive rows (64 B) of one column.  The C tile is read in
+  // batches of 16 values per thread (all loads of a batch issued before the first store) so that the read-modify-write
+  // costs 4 memory round trips per tile, not 64.
   const double alpha = J.alpha, beta = J.beta;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+  for (int gp = 0; gp < 4; ++gp) {
+    double cv[2][2][4];
+    if (beta != 0.0) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = wn * 64 + g * 8 + 2 * lk + e;
-      if (col < J.nrem) {
-        double* cp = J.C + (size_t)col * J.ldc;
+      for (int gg = 0; gg < 2; ++gg)
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          const int row = wm * 32 + f * 8 + lr;
-          if (row < J.mrem) {
-            double v = alpha * acc[f][g][e];
-            if (beta != 0.0) v += beta * cp[row];
-            cp[row] = v;
+        for (int e = 0; e < 2; ++e) {
+          const int col = wn * 64 + (2 * gp + gg) * 8 + 2 * lk + e;
+          const double* cp = J.C + (size_t)col * J.ldc;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int row = wm * 32 + f * 8 + lr;
+            cv[gg][e][f] = (col < J.nrem && row < J.mrem) ? cp[row] : 0.0;
+          }
+        }
+    }
+#pragma unroll
+    for (int gg = 0; gg < 2; ++gg)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int g = 2 * gp + gg;
+        const int col = wn * 64 + g * 8 + 2 * lk + e;
+        if (col < J.nrem) {
+          double* cp = J.C + (size_t)col * J.ldc;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int row = wm * 32 + f * 8 + lr;
+            if (row < J.mrem) {
+              double v = alpha * acc[f][g][e];
+              if (beta != 0.0) v += beta * cv[gg][e][f];
+              cp[row] = v;
+            }
           }
         }
       }
-    }
   }
 }
 

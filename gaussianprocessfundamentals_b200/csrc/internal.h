@@ -10,11 +10,13 @@ namespace gpb {
 extern std::atomic<long long> g_launches;  // kernels launched since load (gpb_launch_count)
 
 struct Exec {
-  cudaStream_t main;
-  cudaStream_t side;       // look-ahead stream of the single-matrix Cholesky
-  cudaEvent_t ev_e[2];     // panel k ready (recorded on main)
+  cudaStream_t main;       // the caller's stream
+  cudaStream_t crit;       // high priority: diagonal block, panel, next panel column (the critical path)
+  cudaStream_t side;       // low priority: the bulk of the trailing update
+  cudaEvent_t ev_fork;     // caller's stream -> crit / side
+  cudaEvent_t ev_e[2];     // panel k ready (recorded on crit)
   cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side)
-  cudaEvent_t ev_join;
+  cudaEvent_t ev_join[2];  // crit / side -> caller's stream
 };
 
 // ---- linalg.cu ------------------------------------------------------------------------------------------------

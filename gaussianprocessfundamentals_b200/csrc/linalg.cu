@@ -160,13 +160,67 @@ struct GeoPlain {
 // diagonal block: Cholesky of a 128 x 128 block in shared memory (+ rows of the carried y^T that fall inside the
 // block), log-det partial, then the block's triangular inverse for the panel product.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int D_LD = 129;
-constexpr int D_SMEM_BYTES = (GPB_NB * D_LD + GPB_NB) * (int)sizeof(double);
+constexpr int D_LD = 132;    // pitch of the block in shared memory (conflict-free DMMA fragment reads)
+constexpr int D_TLD = 68;    // pitch of the 64 x 64 scratch of the in-block inverse
+constexpr int D_SMEM_BYTES = (GPB_NB * D_LD + 64 * D_TLD + 2 * GPB_NB + 16) * (int)sizeof(double);
+
+// Cholesky of the block with the matrix held in registers: thread (lane, warp) owns rows lane+32a (a<4) and columns
+// warp+8b (b<16).  Column j is finished by its owner warp, published through shared memory (double buffered, one
+// barrier per column) and applied as a rank-1 update by everyone; JB = j / 8 is a compile-time constant so that all
+// register indices are static and the update loop shrinks as the factorisation proceeds.
+template <int JB>
+struct PotrfCols {
+  static __device__ __forceinline__ void run(double (&R)[4][16], double* col_s, int warp, int lane, int bf, int row0,
+                                             int* s_info) {
+    if (8 * JB >= bf) return;
+#pragma unroll 1
+    for (int jr = 0; jr < 8; ++jr) {
+      const int j = 8 * JB + jr;
+      if (j >= bf) break;
+      double* cs = col_s + (j & 1) * GPB_NB;
+      if (warp == jr) {
+        const double d = __shfl_sync(0xffffffffu, R[JB >> 2][JB], j & 31);
+        if (!(d > 0.0) && lane == 0 && *s_info == 0) *s_info = row0 + j + 1;
+        // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_jj = d * rsqrt(d): a third of the latency of
+        // sqrt followed by a division on the one chain of the factorisation that cannot be parallelised
+        const double inv = rsqrt(d);
+        const double ljj = d * inv;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int i = lane + 32 * a;
+          double v = R[a][JB] * inv;
+          if (i == j) v = ljj;
+          R[a][JB] = v;
+          cs[i] = v;
+        }
+      }
+      __syncthreads();
+      double lrow[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) lrow[a] = cs[lane + 32 * a];
+#pragma unroll
+      for (int b = JB; b < 16; ++b) {
+        if (b > JB || warp > jr) {
+          const double lc = cs[warp + 8 * b];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) R[a][b] = fma(-lrow[a], lc, R[a][b]);
+        }
+      }
+    }
+    PotrfCols<JB + 1>::run(R, col_s, warp, lane, bf, row0, s_info);
+  }
+};
+template <>
+struct PotrfCols<16> {
+  static __device__ __forceinline__ void run(double (&)[4][16], double*, int, int, int, int, int*) {}
+};
 
 __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__ mats, int k) {
   extern __shared__ __align__(16) double dsm[];
-  double* As = dsm;
-  double* vt = dsm + GPB_NB * D_LD;
+  double* As = dsm;                       // [128][D_LD]   L, then inv(L), column-major
+  double* Ts = As + GPB_NB * D_LD;        // [64][D_TLD]   scratch of the inverse
+  double* col_s = Ts + 64 * D_TLD;        // [2][128]      published column
+  double* red = col_s + 2 * GPB_NB;       // [8]
   __shared__ int s_info;
   const GpbMat d = mats[blockIdx.x];
   const int nrows = d.n + d.aug;
@@ -179,61 +233,98 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
   double* Ag = d.A + r0 + (size_t)r0 * ld;
 
   if (tid == 0) s_info = 0;
-  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
-    const int i = idx & (GPB_NB - 1), j = idx >> 7;
-    double v = 0.0;
-    if (i < bs && j < bs && i >= j) v = Ag[i + (size_t)j * ld];
-    As[i + j * D_LD] = v;
+  double R[4][16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int c = warp + 8 * b;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = lane + 32 * a;
+      R[a][b] = (i < bs && c < bs && i >= c) ? Ag[i + (size_t)c * ld] : 0.0;
+    }
   }
   __syncthreads();
+  PotrfCols<0>::run(R, col_s, warp, lane, bf, r0, &s_info);
 
-  for (int j = 0; j < bf; ++j) {
-    const double ajj = As[j + j * D_LD];
-    if (!(ajj > 0.0) && tid == 0 && s_info == 0) s_info = r0 + j + 1;
-    const double inv = 1.0 / sqrt(ajj);
-    for (int i = j + 1 + tid; i < bs; i += 256) As[i + j * D_LD] *= inv;
-    __syncthreads();
-    for (int c = j + 1 + warp; c < bs; c += 8) {
-      const double lcj = As[c + j * D_LD];
-      for (int i = c + lane; i < bs; i += 32) As[i + c * D_LD] -= As[i + j * D_LD] * lcj;
-    }
-    __syncthreads();
-  }
-  // diagonal: A_jj (fully updated, untouched above) -> L_jj ; log-det partial
+  // write L (zeros above the diagonal by construction) to global and to shared memory; log-det partial
   double lsum = 0.0;
-  if (tid < bf) {
-    const double ljj = sqrt(As[tid + tid * D_LD]);
-    As[tid + tid * D_LD] = ljj;
-    lsum = log(ljj);
-  }
-  if (tid < GPB_NB) vt[tid] = lsum;
-  __syncthreads();
-  if (warp == 0) {
-    double v = vt[lane] + vt[lane + 32] + vt[lane + 64] + vt[lane + 96];
-    v = warp_sum(v);
-    if (lane == 0) {
-      d.part[k] = v;
-      if (s_info != 0 && *d.info == 0) *d.info = s_info;
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    const int c = warp + 8 * b;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = lane + 32 * a;
+      const double v = R[a][b];
+      if (i < bs && c < bs) Ag[i + (size_t)c * ld] = v;
+      if (i == c && i < bf) lsum += log(v);
+      As[i + c * D_LD] = (i < bf && c < bf) ? v : ((i == c) ? 1.0 : 0.0);
     }
   }
-  // write L back (explicit zeros above the diagonal of the block)
-  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
-    const int i = idx & (GPB_NB - 1), j = idx >> 7;
-    if (i < bs && j < bs) Ag[i + (size_t)j * ld] = (i >= j) ? As[i + j * D_LD] : 0.0;
-  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[warp] = lsum;
   __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    d.part[k] = s;
+    if (s_info != 0 && *d.info == 0) *d.info = s_info;
+  }
 
-  // in-place inverse of the bf x bf lower-triangular pivot block (column sweep from the last column)
-  for (int j = bf - 1; j >= 0; --j) {
-    const double wjj = 1.0 / As[j + j * D_LD];
-    for (int i = j + 1 + tid; i < bf; i += 256) vt[i] = As[i + j * D_LD];
-    __syncthreads();
-    for (int i = j + 1 + tid; i < bf; i += 256) {
-      double s = 0.0;
-      for (int kk = j + 1; kk <= i; ++kk) s += As[i + kk * D_LD] * vt[kk];
-      As[i + j * D_LD] = -s * wjj;
+  // ---- in-block inverse: 32 x 32 diagonal blocks by forward substitution in registers (one warp each) ----------
+  if (warp < 4) {
+    const double* Ld = As + (32 * warp) + (32 * warp) * D_LD;
+    double bv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bv[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const double wk = bv[kk] / Ld[kk + kk * D_LD];
+      bv[kk] = wk;
+#pragma unroll
+      for (int i = kk + 1; i < 32; ++i) bv[i] = fma(-Ld[i + kk * D_LD], wk, bv[i]);
     }
-    if (tid == 0) As[j + j * D_LD] = wjj;
+    __syncwarp();
+    double* Wd_ = As + (32 * warp) + (32 * warp + lane) * D_LD;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Wd_[i] = bv[i];
+  }
+  __syncthreads();
+  // ---- recursive doubling on 8 x 8 DMMA tiles: W21 = -W22 * (L21 * W11) for s = 32, 64 --------------------------
+  const int lr = lane >> 2, lk = lane & 3;
+#pragma unroll 1
+  for (int s = 32; s <= 64; s *= 2) {
+    const int ts = s / 8;            // tiles per side of a sub-problem
+    const int nsub = 64 / s;
+    const int ntile = nsub * ts * ts;
+    for (int t = warp; t < ntile; t += 8) {
+      const int p = t / (ts * ts), tt = t % (ts * ts);
+      const int ti = tt / ts, tj = tt % ts;
+      const int b0 = 2 * s * p, rA = b0 + s;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k4 = 2 * tj; k4 < s / 4; ++k4) {
+        const double a = As[(rA + ti * 8 + lr) + (b0 + k4 * 4 + lk) * D_LD];
+        const double b = As[(b0 + k4 * 4 + lk) + (b0 + tj * 8 + lr) * D_LD];
+        dmma884(c0, c1, a, b);
+      }
+      double* tp = Ts + (ti * 8 + lr) + (p * 32 + tj * 8 + 2 * lk) * D_TLD;
+      tp[0] = c0;
+      tp[D_TLD] = c1;
+    }
+    __syncthreads();
+    for (int t = warp; t < ntile; t += 8) {
+      const int p = t / (ts * ts), tt = t % (ts * ts);
+      const int ti = tt / ts, tj = tt % ts;
+      const int b0 = 2 * s * p, rA = b0 + s;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k4 = 0; k4 < 2 * ti + 2; ++k4) {
+        const double a = As[(rA + ti * 8 + lr) + (rA + k4 * 4 + lk) * D_LD];
+        const double b = Ts[(k4 * 4 + lk) + (p * 32 + tj * 8 + lr) * D_TLD];
+        dmma884(c0, c1, a, b);
+      }
+      double* wp = As + (rA + ti * 8 + lr) + (b0 + tj * 8 + 2 * lk) * D_LD;
+      wp[0] = -c0;
+      wp[D_LD] = -c1;
+    }
     __syncthreads();
   }
   double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
@@ -404,7 +495,14 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
   const int nrows = n_max + aug;
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
   const int T_all = (nrows + GPB_NB - 1) / GPB_NB;
-  cudaStream_t ms = ex.main;
+  // With look-ahead the critical path (diagonal block -> panel -> next panel column) runs on a high-priority stream so
+  // that its few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream.
+  cudaStream_t ms = lookahead ? ex.crit : ex.main;
+  if (lookahead) {
+    GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
+    GPB_CK(cudaStreamWaitEvent(ex.crit, ex.ev_fork, 0));
+    GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_fork, 0));
+  }
   for (int k = 0; k < nblk; ++k) {
     diag_kernel<<<B, 256, D_SMEM_BYTES, ms>>>(dm, k);
     ++g_launches;
@@ -425,8 +523,10 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
     GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 2, Tk}, dim3((unsigned)tri_count(Tk, 2, Tk), 1, B), ex.side)));
   }
   if (lookahead) {
-    GPB_CK(cudaEventRecord(ex.ev_join, ex.side));
-    GPB_CK(cudaStreamWaitEvent(ms, ex.ev_join, 0));
+    GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
+    GPB_CK(cudaEventRecord(ex.ev_join[1], ex.side));
+    GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
+    GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
   }
   return cudaSuccess;
 }

@@ -27,6 +27,8 @@ enum GpbOp : int32_t {
   GPB_OP_MAT52 = 5,   // a = hp offset of l            b bit0 = scaled
   GPB_OP_WN = 6,      // no hyper-parameters: 1 where global row index == global column index
   GPB_OP_SE_ARD = 7,  // a = hp offset of l[dim]       b bit0 = scaled (extension; not in the reference)
+  GPB_OP_L2 = 8,      // Euclidean distance itself (Auxiliary/Distances.py:4-7), no hyper-parameters
+  GPB_OP_L1 = 9,      // Manhattan distance itself (Auxiliary/Distances.py:10-12), no hyper-parameters
   GPB_OP_ADD2 = 16,   // pop b, pop a, push a+b
   GPB_OP_MUL2 = 17,   // pop b, pop a, push a*b
   GPB_OP_CPW = 18     // top *= change-point window weight; a = hp offset of cp_0, b = child index, c = #children
@@ -161,6 +163,8 @@ GPB_HD double gpb_leaf(int op, int a, int flags, const GpbPair& p, double* dk) {
       k0 = (p.gi == p.gj) ? 1.0 : 0.0;
       nq = 0;
     } break;
+    case GPB_OP_L2: return sqrt(gpb_sqdist(p));
+    case GPB_OP_L1: return gpb_l1dist(p);
     case GPB_OP_SE_ARD: {
       double r2 = 0.0;
       for (int d = 0; d < p.dim; ++d) { double t = (p.xi[d] - p.xj[d]) / h[d]; r2 += t * t; }
@@ -191,6 +195,8 @@ GPB_HD int gpb_leaf_nhp(int op, int flags, int dim) {
     case GPB_OP_MAT32: nq = 1; break;
     case GPB_OP_MAT52: nq = 1; break;
     case GPB_OP_WN: return 0;
+    case GPB_OP_L2: return 0;
+    case GPB_OP_L1: return 0;
     case GPB_OP_SE_ARD: nq = dim; break;
     default: return 0;
   }

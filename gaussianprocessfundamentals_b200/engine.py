@@ -207,3 +207,32 @@ def gemm(a_kmajor: bool, b_kmajor: bool, A: torch.Tensor, lda: int, Bm: torch.Te
 
 def launch_count() -> int:
     return int(_lib.load().gpb_launch_count())
+
+
+def _padded(t: torch.Tensor) -> torch.Tensor:
+    """row-major 2-d tensor with an even number of columns and 16-byte aligned storage (copy only if needed)"""
+    t = t.contiguous()
+    if t.shape[1] % 2 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    out = torch.zeros((t.shape[0], t.shape[1] + (t.shape[1] % 2)), dtype=torch.float64, device=t.device)
+    out[:, :t.shape[1]].copy_(t)
+    return out
+
+
+def matmul(A: torch.Tensor, Bm: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+    """C = op(A) op(B) for row-major float64 CUDA tensors on the FP64 tensor-core GEMM (gpb_gemm).
+
+    A row-major [r, c] tensor is the column-major c x r matrix with leading dimension c, so C (row-major [m, n]) is
+    computed as the column-major n x m product  C^T = op(B)^T op(A)^T."""
+    require_cuda()
+    m, kk = (A.shape[1], A.shape[0]) if trans_a else (A.shape[0], A.shape[1])
+    k2, n = (Bm.shape[1], Bm.shape[0]) if trans_b else (Bm.shape[0], Bm.shape[1])
+    assert kk == k2, "inner dimensions differ"
+    Ap, Bp = _padded(A), _padded(Bm)
+    C = torch.empty((m, n), dtype=torch.float64, device=A.device)
+    # gemm operand 1 = op(B)^T as an (n x k) matrix: element (j, k) = op(B)[k, j]
+    #   no trans_b: B[k, j] at k*ldB + j  -> MN-major (a_kmajor = 0);  trans_b: B[j, k] at j*ldB + k -> K-major
+    # gemm operand 2 = op(A) as an (m x k) matrix: element (i, k) = op(A)[i, k]
+    #   no trans_a: A[i, k] at i*ldA + k  -> K-major (b_kmajor = 1);   trans_a: A[k, i] at k*ldA + i -> MN-major
+    gemm(bool(trans_b), not trans_a, Bp, Bp.shape[1], Ap, Ap.shape[1], C, n, n, m, kk, 1.0, 0.0)
+    return C

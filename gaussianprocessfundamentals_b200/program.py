@@ -13,13 +13,13 @@ from typing import List, Tuple
 
 import numpy as np
 
-OP = {"SE": 1, "PER": 2, "LIN": 3, "MAT32": 4, "MAT52": 5, "WN": 6, "SE_ARD": 7, "ADD2": 16, "MUL2": 17, "CPW": 18}
+OP = {"SE": 1, "PER": 2, "LIN": 3, "MAT32": 4, "MAT52": 5, "WN": 6, "SE_ARD": 7, "L2": 8, "L1": 9, "ADD2": 16, "MUL2": 17, "CPW": 18}
 MAX_OPS, MAX_STACK, MAX_TAPE, MAX_DIM, MAX_HP = 96, 8, 64, 16, 96
 
 
 def leaf_entries(kind: str, dim: int, scaled: bool) -> List[int]:
     """sizes of the hp list entries of a base kernel (BaseKernels.py get_hyper_parameter_dimensionalities)."""
-    if kind == "WN":
+    if kind in ("WN", "L2", "L1"):
         return []
     if kind == "PER":
         sizes = [1, 1]
@@ -59,9 +59,9 @@ def compile_spec(spec, dim: int, scaled: bool = False) -> CompiledProgram:
 
     def emit(node):
         kind = node[0]
-        if kind in ("SE", "PER", "LIN", "MAT32", "MAT52", "WN", "SE_ARD"):
+        if kind in ("SE", "PER", "LIN", "MAT32", "MAT52", "WN", "SE_ARD", "L2", "L1"):
             sizes = leaf_entries(kind, dim, scaled)
-            ops.append([OP[kind], state["off"], 1 if (scaled and kind != "WN") else 0, 0])
+            ops.append([OP[kind], state["off"], 1 if (scaled and kind not in ("WN", "L2", "L1")) else 0, 0])
             for s in sizes:
                 entries.append((state["off"], s))
                 state["off"] += s

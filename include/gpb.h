@@ -34,6 +34,8 @@ typedef struct gpb_plan gpb_plan_t;
 #define GPB_MAT52 5
 #define GPB_WN 6
 #define GPB_SE_ARD 7
+#define GPB_DIST_L2 8
+#define GPB_DIST_L1 9
 #define GPB_ADD2 16
 #define GPB_MUL2 17
 #define GPB_CPW 18

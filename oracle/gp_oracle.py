@@ -47,7 +47,7 @@ def n_hp_entries(tree, scaled: bool = False) -> int:
         return 1 + (1 if scaled else 0)
     if kind == "PER":
         return 2 + (1 if scaled else 0)
-    if kind == "WN":
+    if kind in ("WN", "L2", "L1"):
         return 0
     if kind in ("ADD", "MUL"):
         return sum(n_hp_entries(c, scaled) for c in tree[1])
@@ -102,6 +102,10 @@ def kernel_matrix(tree, hp: Sequence[torch.Tensor], x: torch.Tensor, x2: torch.T
         q = min(n, m)
         k[:q, :q] = k[:q, :q] + torch.eye(q, dtype=DT)
         return k
+    if kind == "L2":
+        return euclidian_distance(x, x2, reference_distance)
+    if kind == "L1":
+        return manhattan_distance(x, x2)
     if kind == "SE_ARD":  # extension (config C5); equals SE(l=1) on x / l  
         d = (x.unsqueeze(-2) - x2.unsqueeze(-3)) / hp[0]
         k = torch.exp(-0.5 * torch.sum(d * d, -1))

@@ -9,6 +9,7 @@ equivalents of identical IEEE-754 float64 meaning; reverse-mode differentiation 
 
 Nothing in the product package or in the GPU tests imports this module.
 """
+import builtins as _builtins
 import contextlib
 import types
 
@@ -65,7 +66,7 @@ class TensorShape:
 
     def __getitem__(self, i):
         r = self._d[i]
-        return TensorShape(r) if isinstance(i, slice) else r
+        return TensorShape(r) if isinstance(i, _builtins.slice) else r
 
     def __iter__(self):
         return iter(self._d)
@@ -91,7 +92,11 @@ def _raw(x, dtype=None):
         a = _np.asarray(x)
         if a.dtype == _np.float32 or (a.dtype.kind == "f" and dtype is None):
             a = a.astype(_np.float64) if isinstance(x, (float, list, tuple)) or a.dtype == _np.float64 else a
-        t = _torch.from_numpy(_np.ascontiguousarray(a)) if a.ndim else _torch.tensor(a.item())
+        if a.ndim:
+            t = _torch.from_numpy(_np.ascontiguousarray(a))
+        else:  # python / numpy scalar: keep full double precision (torch.tensor(float) would round to float32)
+            t = _torch.tensor(a.item(), dtype=_torch.float64 if a.dtype.kind == "f" else
+                              (_torch.bool if a.dtype.kind == "b" else _torch.int64))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t
@@ -151,7 +156,7 @@ class Tensor:
         return self._t.shape[0]
 
     def __iter__(self):
-        for i in range(self._t.shape[0]):
+        for i in _builtins.range(self._t.shape[0]):
             yield Tensor(self._t[i])
 
     def __float__(self):
@@ -223,7 +228,6 @@ class Tensor:
         return self._bin(o, _torch.ne)
 
 
-import builtins as _builtins  # noqa: E402
 builtins_bool = _builtins.bool
 
 

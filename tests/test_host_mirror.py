@@ -1,0 +1,168 @@
+"""CPU: host-side mirror of the reference's operator surface (no device work): tree utilities, hyper-parameter order,
+defaults, bounds, segment / partition bookkeeping - against the golden vectors of the unmodified reference - and the
+C-ABI library's exported symbols."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import gaussianprocessfundamentals_b200.global_parameters as global_param
+from gaussianprocessfundamentals_b200 import _lib
+from gaussianprocessfundamentals_b200.DataHandling import DataInput as di
+from gaussianprocessfundamentals_b200.KernelBasics import BaseKernels as bk
+from gaussianprocessfundamentals_b200.KernelBasics import Operators as op
+from gaussianprocessfundamentals_b200.KernelBasics import PartitioningModel as pm
+from gaussianprocessfundamentals_b200.KernelBasics import PartitionOperator as po
+from gaussianprocessfundamentals_b200.MeanFunctionBasics import BaseMeanFunctions as bmf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
+LEAF = {"SE": bk.SquaredExponentialKernel, "PER": bk.PeriodicKernel, "LIN": bk.LinearKernel,
+        "MAT32": bk.MaternKernel3_2, "MAT52": bk.MaternKernel5_2, "WN": bk.WhiteNoiseKernel}
+
+
+def build(spec, d=1):
+    kind = spec[0]
+    if kind in LEAF:
+        return LEAF[kind](d)
+    children = [build(c, d) for c in spec[1]]
+    if kind == "ADD":
+        return op.AdditionOperator(d, children)
+    if kind == "MUL":
+        return op.MultiplicationOperator(d, children)
+    if kind == "CP":
+        return op.ChangePointOperator(d, children, [torch.tensor(c, dtype=torch.float64) for c in spec[2]])
+    raise ValueError(kind)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    z = np.load(GOLD)
+    return z, json.loads(bytes(z["__meta__"]).decode("utf-8"))
+
+
+def test_strings_names_and_counts_match_reference(gold):
+    z, meta = gold
+    for name, m in meta.items():
+        if not isinstance(m, dict) or m.get("kind") != "holistic":
+            continue
+        global_param.p_scaled_base_kernel = m["scaled"]
+        try:
+            kern = build(json.loads(m["spec"]))
+            assert kern.get_string_representation() == m["string"], name
+            assert kern.get_hyper_parameter_names(0) == m["names"], name
+            assert kern.get_number_of_hyper_parameter() == int(z[name + "/n_hp"]), name
+        finally:
+            global_param.p_scaled_base_kernel = False
+
+
+def test_sort_changes_hp_order_like_reference(gold):
+    _, meta = gold
+    spec = ["MUL", [["ADD", [["SE"], ["PER"]]], ["LIN"]]]
+    k1, k2 = build(spec), build(spec)
+    assert k1.get_string_representation() == meta["sort_kat"]["before"]
+    assert k1.type_compare_to(k2)
+    assert k1.get_string_representation() == meta["sort_kat"]["after"]
+    assert k1.get_hyper_parameter_names(0) == meta["sort_kat"]["names_after"]
+    assert k1.to_spec() == ("MUL", [("LIN",), ("ADD", [("PER",), ("SE",)])])
+
+
+def test_defaults_and_bounds_match_reference(gold):
+    z, _ = gold
+    kern = build(["MUL", [["ADD", [["SE"], ["PER"]]], ["LIN"]]])
+    xr = [[0.25, 2.25]]
+    d = np.concatenate([h.numpy().reshape(-1) for h in kern.get_default_hyper_parameter(xr, 500)])
+    assert np.array_equal(d, z["defaults/composite"])
+    b = kern.get_hyper_parameter_bounds(xr, 500)
+    lo = np.concatenate([np.asarray(v[0]).reshape(-1) for v in b])
+    hi = np.concatenate([np.asarray(v[1]).reshape(-1) for v in b])
+    assert np.allclose(lo, z["bounds/composite_lo"], rtol=1e-15, atol=0, equal_nan=True)
+    assert np.allclose(hi, z["bounds/composite_hi"], rtol=1e-15, atol=0, equal_nan=True)
+
+
+def test_blockwise_segments_bit_exact(gold):
+    z, _ = gold
+    x, y, cps = z["blockwise/x"], z["blockwise/y"], z["blockwise/cps"]
+    b = di.BlockwiseDataInput(x, y, x, y, [torch.tensor(c, dtype=torch.float64) for c in cps])
+    assert len(b.data_inputs) == len(cps) + 1
+    for i, blk in enumerate(b.data_inputs):
+        assert blk.n_train == int(z["blockwise/seg%d_n" % i])
+        assert np.array_equal(blk.data_x_train.numpy(), z["blockwise/seg%d_x" % i])
+
+
+def test_partition_indices_and_reordering_bit_exact(gold):
+    z, _ = gold
+    x, y, edges = z["partition/x"], z["partition/y"], z["partition/edges"]
+    model = pm.PartitioningModel(pm.PartitioningClass.SELF_SUFFICIENT, [])
+    model.init_partitioning([pm.IntervalCriterion(edges[i], edges[i + 1]) for i in range(4)])
+    idx = model.get_data_record_indices_per_partition(x)
+    for i, ix in enumerate(idx):
+        assert np.array_equal(np.asarray(ix, dtype=np.int64), z["partition/idx%d" % i])
+    pdi = model.partition_data_input(di.DataInput(x, y, x, y))
+    assert np.array_equal(pdi.data_x_train.numpy(), z["partition/x_reordered"])
+    assert [blk.n_train for blk in pdi.data_inputs] == [len(z["partition/idx%d" % i]) for i in range(4)]
+    copy = model.deepcopy()
+    assert copy.get_number_of_partitions() == 4 and copy.partition_class == model.partition_class
+
+
+def test_child_slices_advance_over_change_points_and_empty_blocks():
+    kern = build(["CP", [["SE"], ["PER"], ["ADD", [["SE"], ["LIN"]]]], [0.3, 0.6]])
+    assert kern.get_number_of_hyper_parameter() == 2 + 1 + 2 + 2
+    assert [(s.start, s.stop) for s in kern.child_slices()] == [(2, 3), (3, 5), (5, 7)]
+    hp = kern.get_default_hyper_parameter([[0.0, 1.0]], 100)
+    assert [float(h.reshape(-1)[0]) for h in hp[:2]] == [0.3, 0.6]
+    kern.set_last_hyper_parameter(hp)
+    assert len(kern.get_last_hyper_parameter()) == 7
+
+
+def test_simplification_and_pruning():
+    se, per, lin = bk.SquaredExponentialKernel(1), bk.PeriodicKernel(1), bk.LinearKernel(1)
+    prod = op.MultiplicationOperator(1, [op.AdditionOperator(1, [se, per]), lin])
+    assert prod.get_simplified_version().get_string_representation() == "((LIN x SE) + (LIN x PER))"
+    cp = build(["CP", [["SE"], ["PER"], ["LIN"]], [0.4, 1.7]])
+    pruned, changed = cp.get_simplified_kernel([0.0, 1.0])
+    assert changed and pruned.get_string_representation() == "(SE ][ PER)"
+    same, changed = build(["CP", [["SE"], ["PER"]], [0.4]]).get_simplified_kernel([0.0, 1.0])
+    assert not changed
+
+
+def test_unscaling_of_fitted_hyper_parameters():
+    se, per, lin = bk.SquaredExponentialKernel(1), bk.PeriodicKernel(1), bk.LinearKernel(1)
+    k = op.AdditionOperator(1, [se, per, lin])
+    k.set_last_hyper_parameter([torch.tensor(-0.2, dtype=torch.float64), torch.tensor(0.3, dtype=torch.float64),
+                                torch.tensor(-0.4, dtype=torch.float64), torch.tensor([0.5], dtype=torch.float64)])
+    raw = [float(h.reshape(-1)[0]) for h in k.get_last_hyper_parameter()]
+    assert raw == [0.2, 0.3, 0.4, 0.5]            # |l|, |p| are stored (BaseKernels.py:429-432, :629-634)
+    sc = [float(h.reshape(-1)[0]) for h in k.get_last_hyper_parameter((10.0, 2.0))]
+    assert sc == [0.4, 0.6, 0.8, 0.5 * 2.0 + 10.0]  # l*s1, l*s1, p*s1, c*s1+s0 (BaseKernels.py:259-269,417-427,617-627)
+
+
+def test_library_exports_every_declared_symbol():
+    """the C-ABI shared library loads on a machine without a GPU and exports what include/gpb.h declares"""
+    header = open(os.path.join(ROOT, "include", "gpb.h")).read()
+    declared = set(re.findall(r"\b(gpb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.gpb_version.restype = ctypes.c_int
+    assert lib.gpb_version() >= 100
+
+
+def test_no_cpu_fallback():
+    from gaussianprocessfundamentals_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.GpbError):
+        engine.require_cuda()
+    kern = bk.SquaredExponentialKernel(1)
+    x = np.linspace(0, 1, 8)[:, None]
+    with pytest.raises(_lib.GpbError):
+        kern.get_tf_tensor([torch.tensor(0.1, dtype=torch.float64)], x, x)
