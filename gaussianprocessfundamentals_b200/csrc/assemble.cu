@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __r
   const GpbMat& d = mats[blockIdx.z];
   const int T = (d.n + A_T - 1) / A_T;
   int ti, tj;
-  if (!tri_map(blockIdx.x, T, 0, T, ti, tj)) return;
+  if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
   AsmArgs a;
   a.code = d.code; a.n_ops = d.n_ops; a.dim = d.dim; a.cp_mode = d.cp_mode;
   a.X = d.X; a.X2 = nullptr; a.n = d.n; a.m = d.n; a.hp = d.hp; a.n_hp = d.n_hp; a.noise = d.noise;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) assemble_rect_kernel(const AsmArgs a) {
   const int Tm = (int)((a.n + A_T - 1) / A_T);
   if (a.lower_only) {
     int ti, tj;
-    if (!tri_map(blockIdx.x, Tm, 0, Tm, ti, tj)) return;
+    if (!tri_map(blockIdx.x, Tm, 1, 0, Tm, ti, tj)) return;
     assemble_tile(a, ti, tj, Tm);
   } else {
     assemble_tile(a, blockIdx.x, blockIdx.y, Tm);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   const GpbMat& d = mats[blockIdx.z];
   const int T = (d.n + A_T - 1) / A_T;
   int ti, tj;
-  if (!tri_map(blockIdx.x, T, 0, T, ti, tj)) return;
+  if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
   const int P = d.n_hp + 1;
   double* s_acc = reinterpret_cast<double*>(g_smem);            // [acc_stride][256]
   double* s_hp = s_acc + (size_t)acc_stride * 256;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const GpbMat* __restri
 
 int grad_tiles(int n) {
   const int T = (n + A_T - 1) / A_T;
-  return (int)tri_count(T, 0, T);
+  return (int)tri_count(T, 1, 0, T);
 }
 
 static size_t grad_smem_bytes(int n_ops_max, int n_hp_max, int dim) {
@@ -214,7 +214,7 @@ cudaError_t assemble_init() {
 cudaError_t run_assemble_batched(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
   const int T = (n_max + A_T - 1) / A_T;
   const size_t smem = asm_smem_bytes(GPB_MAX_OPS, GPB_MAX_HP, GPB_MAX_DIM);
-  assemble_batched_kernel<<<dim3((unsigned)tri_count(T, 0, T), 1, B), 256, smem, s>>>(dm);
+  assemble_batched_kernel<<<dim3((unsigned)tri_count(T, 1, 0, T), 1, B), 256, smem, s>>>(dm);
   ++g_launches;
   return cudaGetLastError();
 }
@@ -229,7 +229,7 @@ cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int c
   const int Tm = (int)((n + A_T - 1) / A_T), Tn = (int)((m + A_T - 1) / A_T);
   if (Tm == 0 || Tn == 0) return cudaSuccess;
   const size_t smem = asm_smem_bytes(n_ops, n_hp, dim);
-  dim3 grid = lower_only ? dim3((unsigned)tri_count(Tm, 0, Tm), 1, 1) : dim3(Tm, Tn, 1);
+  dim3 grid = lower_only ? dim3((unsigned)tri_count(Tm, 1, 0, Tm), 1, 1) : dim3(Tm, Tn, 1);
   assemble_rect_kernel<<<grid, 256, smem, s>>>(a);
   ++g_launches;
   return cudaGetLastError();

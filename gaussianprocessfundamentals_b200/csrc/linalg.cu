@@ -8,36 +8,38 @@
 //                the pieces of dNLL/dK = 1/2 (K^-1 - alpha alpha^T) that TF's Cholesky gradient produces for
 //                Optimizer/Fitter.py:124-158.
 //   run_trsv     standalone forward/back substitution (CovarianceMatrix.py:260-262) for get_L_alpha().
+#include <cstdlib>
 #include "gemm.cuh"
 #include "internal.h"
 
 namespace gpb {
 
 // ---------------------------------------------------------------------------------------------------------------
-// GEMM geometries
+// GEMM geometries (tile<BM, BN>() fills the job of the calling CTA; BN is always 128 = GPB_NB)
 // ---------------------------------------------------------------------------------------------------------------
 
-// trailing update of step k: A[r0:, r0:] -= P P^T with P = A[r0:, k*128 : (k+1)*128], lower tiles, tile columns
+// trailing update of step k: A[r0:, r0:] -= P P^T with P = A[r0:, k*128 : k*128 + kw], lower tiles, tile columns
 // restricted to [c_lo, c_hi) so that the look-ahead driver can split the update across streams.
 struct GeoSyrk {
   const GpbMat* mats;
   int k, c_lo, c_hi;
-  __device__ bool operator()(TileJob& J) const {
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
     const GpbMat& d = mats[blockIdx.z];
     const int nrows = d.n + d.aug;
     const int r0 = (k + 1) * GPB_NB;
     if (r0 >= nrows || (k + 1) * GPB_NB > d.n) return false;
-    const int T = (nrows - r0 + GPB_NB - 1) / GPB_NB;
+    const int Tm = (nrows - r0 + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(blockIdx.x, T, c_lo, c_hi, ti, tj)) return false;
+    if (!tri_map(blockIdx.x, Tm, BN / BM, c_lo, c_hi, ti, tj)) return false;
     const size_t ld = d.ld;
     const double* P = d.A + (size_t)k * GPB_NB * ld;
-    J.A = P + r0 + ti * GPB_NB;
-    J.B = P + r0 + tj * GPB_NB;
-    J.C = d.A + (r0 + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.A = P + r0 + ti * BM;
+    J.B = P + r0 + tj * BN;
+    J.C = d.A + (r0 + ti * BM) + (size_t)(r0 + tj * BN) * ld;
     J.lda = J.ldb = J.ldc = d.ld;
-    J.mrem = min(GPB_NB, nrows - r0 - ti * GPB_NB);
-    J.nrem = min(GPB_NB, nrows - r0 - tj * GPB_NB);
+    J.mrem = min(BM, nrows - r0 - ti * BM);
+    J.nrem = min(BN, nrows - r0 - tj * BN);
     J.klo = 0; J.khi = GPB_NB;
     J.alpha = -1.0; J.beta = 1.0;
     return true;
@@ -45,22 +47,25 @@ struct GeoSyrk {
 };
 
 // panel solve of step k as a product with the inverted diagonal block: A[r0:, kblk] = A[r0:, kblk] * Wd_k^T
+// (in place: a CTA owns all 128 columns of its rows, so BN must be 128)
 struct GeoPanel {
   const GpbMat* mats;
   int k;
-  __device__ bool operator()(TileJob& J) const {
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
+    static_assert(BN == GPB_NB, "the in-place panel product needs full-width tiles");
     const GpbMat& d = mats[blockIdx.z];
     const int nrows = d.n + d.aug;
     const int r0 = (k + 1) * GPB_NB;
     if (r0 > d.n) return false;  // block k is not a full pivot block
-    const int i0 = r0 + blockIdx.x * GPB_NB;
+    const int i0 = r0 + blockIdx.x * BM;
     if (i0 >= nrows) return false;
     const size_t ld = d.ld;
     double* P = d.A + (size_t)k * GPB_NB * ld + i0;
     J.A = P; J.C = P;
     J.B = d.Wd + (size_t)k * GPB_NB * GPB_NB;
     J.lda = J.ldc = d.ld; J.ldb = GPB_NB;
-    J.mrem = min(GPB_NB, nrows - i0);
+    J.mrem = min(BM, nrows - i0);
     J.nrem = GPB_NB;
     J.klo = 0; J.khi = GPB_NB;
     J.alpha = 1.0; J.beta = 0.0;
@@ -74,22 +79,23 @@ struct GeoPanel {
 struct GeoTrtriT {
   const GpbMat* mats;
   int s;
-  __device__ bool operator()(TileJob& J) const {
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
     const GpbMat& d = mats[blockIdx.z];
     const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
-    const int ts = s / GPB_NB;
-    const int ti = blockIdx.x / ts, tj = blockIdx.x % ts;
-    if (ti * GPB_NB >= M) return false;
+    const int tsn = s / BN;
+    const int ti = blockIdx.x / tsn, tj = blockIdx.x % tsn;
+    if (ti * BM >= M) return false;
     const size_t ld = d.ld;
-    J.A = d.A + (rA + ti * GPB_NB) + (size_t)r0 * ld;
-    J.B = d.A + r0 + (size_t)(r0 + tj * GPB_NB) * ld;
-    J.C = d.Kinv + (rA + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.A = d.A + (rA + ti * BM) + (size_t)r0 * ld;
+    J.B = d.A + r0 + (size_t)(r0 + tj * BN) * ld;
+    J.C = d.Kinv + (rA + ti * BM) + (size_t)(r0 + tj * BN) * ld;
     J.lda = J.ldb = J.ldc = d.ld;
-    J.mrem = min(GPB_NB, M - ti * GPB_NB);
-    J.nrem = GPB_NB;
-    J.klo = tj * GPB_NB; J.khi = s;
+    J.mrem = min(BM, M - ti * BM);
+    J.nrem = BN;
+    J.klo = tj * BN; J.khi = s;
     J.alpha = 1.0; J.beta = 0.0;
     return true;
   }
@@ -98,22 +104,23 @@ struct GeoTrtriT {
 struct GeoTrtriW {
   const GpbMat* mats;
   int s;
-  __device__ bool operator()(TileJob& J) const {
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
     const GpbMat& d = mats[blockIdx.z];
     const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
-    const int ts = s / GPB_NB;
-    const int ti = blockIdx.x / ts, tj = blockIdx.x % ts;
-    if (ti * GPB_NB >= M) return false;
+    const int tsn = s / BN;
+    const int ti = blockIdx.x / tsn, tj = blockIdx.x % tsn;
+    if (ti * BM >= M) return false;
     const size_t ld = d.ld;
-    J.A = d.A + (rA + ti * GPB_NB) + (size_t)rA * ld;
-    J.B = d.Kinv + rA + (size_t)(r0 + tj * GPB_NB) * ld;
-    J.C = d.A + (rA + ti * GPB_NB) + (size_t)(r0 + tj * GPB_NB) * ld;
+    J.A = d.A + (rA + ti * BM) + (size_t)rA * ld;
+    J.B = d.Kinv + rA + (size_t)(r0 + tj * BN) * ld;
+    J.C = d.A + (rA + ti * BM) + (size_t)(r0 + tj * BN) * ld;
     J.lda = J.ldb = J.ldc = d.ld;
-    J.mrem = min(GPB_NB, M - ti * GPB_NB);
-    J.nrem = GPB_NB;
-    J.klo = 0; J.khi = min(M, (ti + 1) * GPB_NB);
+    J.mrem = min(BM, M - ti * BM);
+    J.nrem = BN;
+    J.klo = 0; J.khi = min(M, (ti + 1) * BM);
     J.alpha = -1.0; J.beta = 0.0;
     return true;
   }
@@ -122,19 +129,20 @@ struct GeoTrtriW {
 // inv(K) = W^T W, lower tiles only, k >= tile row start (W lower triangular), out of place into Kinv
 struct GeoLauum {
   const GpbMat* mats;
-  __device__ bool operator()(TileJob& J) const {
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
     const GpbMat& d = mats[blockIdx.z];
-    const int T = (d.n + GPB_NB - 1) / GPB_NB;
+    const int Tm = (d.n + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(blockIdx.x, T, 0, T, ti, tj)) return false;
+    if (!tri_map(blockIdx.x, Tm, BN / BM, 0, Tm, ti, tj)) return false;
     const size_t ld = d.ld;
-    J.A = d.A + (size_t)(ti * GPB_NB) * ld;
-    J.B = d.A + (size_t)(tj * GPB_NB) * ld;
-    J.C = d.Kinv + ti * GPB_NB + (size_t)(tj * GPB_NB) * ld;
+    J.A = d.A + (size_t)(ti * BM) * ld;
+    J.B = d.A + (size_t)(tj * BN) * ld;
+    J.C = d.Kinv + ti * BM + (size_t)(tj * BN) * ld;
     J.lda = J.ldb = J.ldc = d.ld;
-    J.mrem = min(GPB_NB, d.n - ti * GPB_NB);
-    J.nrem = min(GPB_NB, d.n - tj * GPB_NB);
-    J.klo = ti * GPB_NB; J.khi = d.n;
+    J.mrem = min(BM, d.n - ti * BM);
+    J.nrem = min(BN, d.n - tj * BN);
+    J.klo = ti * BM; J.khi = d.n;
     J.alpha = 1.0; J.beta = 0.0;
     return true;
   }
@@ -144,13 +152,14 @@ struct GeoPlain {
   const double* A; const double* B; double* C;
   int lda, ldb, ldc, M, N, K, akm, bkm;
   double alpha, beta;
-  __device__ bool operator()(TileJob& J) const {
-    const int i0 = blockIdx.x * GPB_NB, j0 = blockIdx.y * GPB_NB;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
+    const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
     J.A = akm ? A + (size_t)i0 * lda : A + i0;
     J.B = bkm ? B + (size_t)j0 * ldb : B + j0;
     J.C = C + i0 + (size_t)j0 * ldc;
     J.lda = lda; J.ldb = ldb; J.ldc = ldc;
-    J.mrem = min(GPB_NB, M - i0); J.nrem = min(GPB_NB, N - j0);
+    J.mrem = min(BM, M - i0); J.nrem = min(BN, N - j0);
     J.klo = 0; J.khi = K; J.alpha = alpha; J.beta = beta;
     return true;
   }
@@ -464,37 +473,55 @@ __global__ void symmetrize_kernel(double* A, int n, int ld) {
 // ---------------------------------------------------------------------------------------------------------------
 #define GPB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-template <bool AKM, bool BKM, class Geo>
-static cudaError_t launch_gemm(const Geo& geo, dim3 grid, cudaStream_t s) {
+// tile configuration used by the drivers: GPB_GEMM_CFG=big|half (default half)
+static int g_cfg_half = -1;
+static bool cfg_half() {
+  if (g_cfg_half < 0) {
+    const char* e = getenv("GPB_GEMM_CFG");
+    g_cfg_half = (e && e[0] == 'b') ? 0 : 1;
+  }
+  return g_cfg_half == 1;
+}
+
+template <class Cfg, bool AKM, bool BKM, class Geo>
+static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
-  gemm_kernel<AKM, BKM, Geo><<<grid, G_THREADS, G_SMEM_BYTES, s>>>(geo);
+  gemm_kernel<Cfg, AKM, BKM, Geo><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo);
   ++g_launches;
   return cudaGetLastError();
 }
 
-template <bool AKM, bool BKM, class Geo>
+template <class Cfg, bool AKM, bool BKM, class Geo>
 static cudaError_t set_smem() {
-  return cudaFuncSetAttribute(gemm_kernel<AKM, BKM, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+  return cudaFuncSetAttribute(gemm_kernel<Cfg, AKM, BKM, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg::SMEM_BYTES);
+}
+template <class Cfg>
+static cudaError_t set_smem_all() {
+  GPB_CK((set_smem<Cfg, false, false, GeoSyrk>()));
+  GPB_CK((set_smem<Cfg, false, false, GeoPanel>()));
+  GPB_CK((set_smem<Cfg, false, true, GeoTrtriT>()));
+  GPB_CK((set_smem<Cfg, false, true, GeoTrtriW>()));
+  GPB_CK((set_smem<Cfg, true, true, GeoLauum>()));
+  GPB_CK((set_smem<Cfg, false, false, GeoPlain>()));
+  GPB_CK((set_smem<Cfg, false, true, GeoPlain>()));
+  GPB_CK((set_smem<Cfg, true, false, GeoPlain>()));
+  GPB_CK((set_smem<Cfg, true, true, GeoPlain>()));
+  return cudaSuccess;
 }
 
 cudaError_t linalg_init() {
-  GPB_CK((set_smem<false, false, GeoSyrk>()));
-  GPB_CK((set_smem<false, false, GeoPanel>()));
-  GPB_CK((set_smem<false, true, GeoTrtriT>()));
-  GPB_CK((set_smem<false, true, GeoTrtriW>()));
-  GPB_CK((set_smem<true, true, GeoLauum>()));
-  GPB_CK((set_smem<false, false, GeoPlain>()));
-  GPB_CK((set_smem<false, true, GeoPlain>()));
-  GPB_CK((set_smem<true, false, GeoPlain>()));
-  GPB_CK((set_smem<true, true, GeoPlain>()));
+  GPB_CK(set_smem_all<CfgBig>());
+  GPB_CK(set_smem_all<CfgHalf>());
   GPB_CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
   return cudaSuccess;
 }
 
-cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
+template <class Cfg>
+static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
+  constexpr int BM = Cfg::BM, R = Cfg::BN / Cfg::BM;
   const int nrows = n_max + aug;
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
-  const int T_all = (nrows + GPB_NB - 1) / GPB_NB;
   // With look-ahead the critical path (diagonal block -> panel -> next panel column) runs on a high-priority stream so
   // that its few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream.
   cudaStream_t ms = lookahead ? ex.crit : ex.main;
@@ -507,20 +534,22 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
     diag_kernel<<<B, 256, D_SMEM_BYTES, ms>>>(dm, k);
     ++g_launches;
     GPB_CK(cudaGetLastError());
-    const int Tk = T_all - (k + 1);
-    if (Tk <= 0 || (k + 1) * GPB_NB > n_max) continue;
-    GPB_CK((launch_gemm<false, false>(GeoPanel{dm, k}, dim3(Tk, 1, B), ms)));
+    const int rows = nrows - (k + 1) * GPB_NB;   // rows below the diagonal block
+    if (rows <= 0 || (k + 1) * GPB_NB > n_max) continue;
+    const int Tm = (rows + BM - 1) / BM;
+    const int Tn = (rows + GPB_NB - 1) / GPB_NB;
+    GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms)));
     if (!lookahead) {
-      GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 0, Tk}, dim3((unsigned)tri_count(Tk, 0, Tk), 1, B), ms)));
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, Tn}, dim3((unsigned)tri_count(Tm, R, 0, Tn), 1, B), ms)));
       continue;
     }
     if (k > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(k - 1) & 1], 0));
-    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 0, 1}, dim3((unsigned)tri_count(Tk, 0, 1), 1, B), ms)));
+    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, 1}, dim3((unsigned)tri_count(Tm, R, 0, 1), 1, B), ms)));
     GPB_CK(cudaEventRecord(ex.ev_e[k & 1], ms));
     GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[k & 1], 0));
-    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 1, 2}, dim3((unsigned)tri_count(Tk, 1, 2), 1, B), ex.side)));
+    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 1, 2}, dim3((unsigned)tri_count(Tm, R, 1, 2), 1, B), ex.side)));
     GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ex.side));
-    GPB_CK((launch_gemm<false, false>(GeoSyrk{dm, k, 2, Tk}, dim3((unsigned)tri_count(Tk, 2, Tk), 1, B), ex.side)));
+    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 2, Tn}, dim3((unsigned)tri_count(Tm, R, 2, Tn), 1, B), ex.side)));
   }
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
@@ -531,24 +560,33 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
   return cudaSuccess;
 }
 
+cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
+  return cfg_half() ? potrf_impl<CfgHalf>(dm, B, n_max, aug, lookahead, ex)
+                    : potrf_impl<CfgBig>(dm, B, n_max, aug, lookahead, ex);
+}
+
 cudaError_t run_finalize(const GpbMat* dm, int B, double log2pi, cudaStream_t s) {
   finalize_kernel<<<B, 256, 0, s>>>(dm, log2pi);
   ++g_launches;
   return cudaGetLastError();
 }
 
-cudaError_t run_trtri(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+template <class Cfg>
+static cudaError_t trtri_impl(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
   diag_copy_kernel<<<dim3(nblk, B), 256, 0, s>>>(dm);
   ++g_launches;
   GPB_CK(cudaGetLastError());
   for (long long sz = GPB_NB; sz < n_max; sz *= 2) {
-    const int ts = (int)(sz / GPB_NB);
+    const int tiles = (int)(sz / Cfg::BM) * (int)(sz / Cfg::BN);
     const int nsub = (int)((n_max + 2 * sz - 1) / (2 * sz));
-    GPB_CK((launch_gemm<false, true>(GeoTrtriT{dm, (int)sz}, dim3(ts * ts, nsub, B), s)));
-    GPB_CK((launch_gemm<false, true>(GeoTrtriW{dm, (int)sz}, dim3(ts * ts, nsub, B), s)));
+    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriT{dm, (int)sz}, dim3(tiles, nsub, B), s)));
+    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriW{dm, (int)sz}, dim3(tiles, nsub, B), s)));
   }
   return cudaSuccess;
+}
+cudaError_t run_trtri(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+  return cfg_half() ? trtri_impl<CfgHalf>(dm, B, n_max, s) : trtri_impl<CfgBig>(dm, B, n_max, s);
 }
 
 cudaError_t run_alpha(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
@@ -557,9 +595,13 @@ cudaError_t run_alpha(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <class Cfg>
+static cudaError_t lauum_impl(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+  const int Tm = (n_max + Cfg::BM - 1) / Cfg::BM;
+  return launch_cfg<Cfg, true, true>(GeoLauum{dm}, dim3((unsigned)tri_count(Tm, Cfg::BN / Cfg::BM, 0, Tm), 1, B), s);
+}
 cudaError_t run_lauum(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
-  const int T = (n_max + GPB_NB - 1) / GPB_NB;
-  return launch_gemm<true, true>(GeoLauum{dm}, dim3((unsigned)tri_count(T, 0, T), 1, B), s);
+  return cfg_half() ? lauum_impl<CfgHalf>(dm, B, n_max, s) : lauum_impl<CfgBig>(dm, B, n_max, s);
 }
 
 cudaError_t run_trsv(const GpbMat* dm, int B, int n_max, int transposed, cudaStream_t s) {
@@ -630,14 +672,21 @@ cudaError_t run_microbench(int kind, int iters, int blocks, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <class Cfg>
+static cudaError_t plain_impl(const GeoPlain& g, int M, int N, cudaStream_t s) {
+  dim3 grid((M + Cfg::BM - 1) / Cfg::BM, (N + Cfg::BN - 1) / Cfg::BN, 1);
+  if (!g.akm && !g.bkm) return launch_cfg<Cfg, false, false>(g, grid, s);
+  if (!g.akm && g.bkm) return launch_cfg<Cfg, false, true>(g, grid, s);
+  if (g.akm && !g.bkm) return launch_cfg<Cfg, true, false>(g, grid, s);
+  return launch_cfg<Cfg, true, true>(g, grid, s);
+}
 cudaError_t run_gemm_plain(int akm, int bkm, const double* A, int lda, const double* Bm, int ldb, double* C, int ldc,
                            int M, int N, int K, double alpha, double beta, cudaStream_t s) {
-  GeoPlain g{A, Bm, C, lda, ldb, ldc, M, N, K, akm, bkm, alpha, beta};
-  dim3 grid((M + GPB_NB - 1) / GPB_NB, (N + GPB_NB - 1) / GPB_NB, 1);
-  if (!akm && !bkm) return launch_gemm<false, false>(g, grid, s);
-  if (!akm && bkm) return launch_gemm<false, true>(g, grid, s);
-  if (akm && !bkm) return launch_gemm<true, false>(g, grid, s);
-  return launch_gemm<true, true>(g, grid, s);
+  GeoPlain g{A, Bm, C, lda, ldb, ldc, M, N, K, akm & 1, bkm & 1, alpha, beta};
+  // akm bits 1-2 select the tile configuration explicitly (tests / probes): +0 driver default, +2 big, +4 half
+  const int sel = akm >> 1;
+  const bool half = sel == 0 ? cfg_half() : (sel == 2);
+  return half ? plain_impl<CfgHalf>(g, M, N, s) : plain_impl<CfgBig>(g, M, N, s);
 }
 
 }  // namespace gpb

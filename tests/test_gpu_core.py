@@ -50,9 +50,10 @@ def _flat(entries_hp):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [2, 4])   # 128x128 tiles / 64x128 tiles (csrc/gemm.cuh)
 @pytest.mark.parametrize("akm,bkm", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("shape", [(128, 128, 128), (300, 200, 150), (257, 129, 151), (64, 1, 16), (1, 5, 7)])
-def test_gemm_dmma(akm, bkm, shape):
+def test_gemm_dmma(akm, bkm, shape, cfg):
     eng = _eng()
     M, N, K = shape
     rng = np.random.default_rng(M * 7 + N * 3 + K)
@@ -77,14 +78,14 @@ def test_gemm_dmma(akm, bkm, shape):
         Ch[i + np.arange(N) * ldc] = C0[i, :]
     dev = torch.device("cuda")
     At, Bt, Ct = (torch.tensor(v, dtype=torch.float64, device=dev) for v in (Ah, Bh, Ch))
-    eng.gemm(akm, bkm, At, lda, Bt, ldb, Ct, ldc, M, N, K, -0.75, 0.5)
+    eng.gemm(akm | cfg, bkm, At, lda, Bt, ldb, Ct, ldc, M, N, K, -0.75, 0.5)
     got = Ct.cpu().numpy()
     want = -0.75 * A @ Bm.T + 0.5 * C0
     res = np.array([[got[i + j * ldc] for j in range(N)] for i in range(M)])
     assert np.max(np.abs(res - want)) <= 1e-12 * max(1.0, np.max(np.abs(want))) * K
     # beta == 0 must ignore NaNs in C
     Ct2 = torch.full_like(Ct, float("nan"))
-    eng.gemm(akm, bkm, At, lda, Bt, ldb, Ct2, ldc, M, N, K, 1.0, 0.0)
+    eng.gemm(akm | cfg, bkm, At, lda, Bt, ldb, Ct2, ldc, M, N, K, 1.0, 0.0)
     got2 = Ct2.cpu().numpy()
     res2 = np.array([[got2[i + j * ldc] for j in range(N)] for i in range(M)])
     assert np.max(np.abs(res2 - A @ Bm.T)) <= 1e-12 * K * max(1.0, np.max(np.abs(A @ Bm.T)))

@@ -54,9 +54,13 @@ def main():
     c = torch.empty(n, n, dtype=torch.float64, device=dev)
     t, tm = timed(lambda: torch.matmul(a, b, out=c))
     emit(what="cublas_dgemm_8192", ms=t, ms_median=tm, tflops=2 * n ** 3 / (t * 1e-3) / 1e12)
-    for akm, bkm in ((0, 0), (0, 1), (1, 1)):
-        t, tm = timed(lambda: eng.gemm(akm, bkm, a, n, b, n, c, n, n, n, n, 1.0, 0.0))
-        emit(what="gpb_gemm_8192", akm=akm, bkm=bkm, ms=t, ms_median=tm, tflops=2 * n ** 3 / (t * 1e-3) / 1e12)
+    for cfg in (2, 4):
+        for akm, bkm in ((0, 0), (0, 1), (1, 1)):
+            t, tm = timed(lambda: eng.gemm(akm | cfg, bkm, a, n, b, n, c, n, n, n, n, 1.0, 0.0))
+            emit(what="gpb_gemm_8192", cfg={2: "big", 4: "half"}[cfg], akm=akm, bkm=bkm, ms=t, ms_median=tm,
+                 tflops=2 * n ** 3 / (t * 1e-3) / 1e12)
+        t, tm = timed(lambda: eng.gemm(cfg, 0, a, n, b, n, c, n, n, n, 128, -1.0, 1.0))
+        emit(what="gpb_gemm_8192_k128_rmw", cfg={2: "big", 4: "half"}[cfg], ms=t, tflops=2 * n * n * 128 / (t * 1e-3) / 1e12)
     spd = a @ a.t() + n * torch.eye(n, dtype=torch.float64, device=dev)
     t, tm = timed(lambda: torch.linalg.cholesky(spd))
     emit(what="cusolver_potrf_8192", ms=t, tflops=n ** 3 / 3 / (t * 1e-3) / 1e12)
