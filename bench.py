@@ -257,16 +257,18 @@ def main():
         return torch.cuda.Event(enable_timing=True)
     stage_ms = {}
     for _ in range(2):
-        marks = [ev() for _ in range(6)]
+        marks = [ev() for _ in range(7)]
         marks[0].record()
         plan.eval(eng.STAGE_ASSEMBLE); marks[1].record()
         plan.eval(eng.STAGE_POTRF); marks[2].record()
         plan.eval(eng.STAGE_NLL); marks[3].record()
-        plan.eval(eng.STAGE_INVERSE); marks[4].record()
-        plan.eval(eng.STAGE_GRAD); marks[5].record()
+        plan.eval(eng.STAGE_TRTRI); marks[4].record()
+        plan.eval(eng.STAGE_LAUUM); marks[5].record()      # ONE launch: Kinv = W^T W, the roofline kernel
+        plan.eval(eng.STAGE_GRAD); marks[6].record()
         torch.cuda.synchronize()
-        for i, name in enumerate(["assemble", "potrf", "nll", "inverse", "grad"]):
+        for i, name in enumerate(["assemble", "potrf", "nll", "trtri", "lauum", "grad"]):
             stage_ms[name] = marks[i].elapsed_time(marks[i + 1])
+        stage_ms["inverse"] = stage_ms["trtri"] + stage_ms["lauum"]
 
     # ---- FP64 peak, measured live (MEASURED_PEAKS.json carries no FP64 entry) --------------------------------------------
     lib = _lib.load()
@@ -364,6 +366,8 @@ def main():
         tf_potrf = flops_potrf / (stage_ms["potrf"] * 1e-3) / 1e12
         tf_inv = flops_inv / (stage_ms["inverse"] * 1e-3) / 1e12
         tf_all = (flops_potrf + flops_inv) / ((stage_ms["potrf"] + stage_ms["inverse"]) * 1e-3) / 1e12
+        flops_lauum = n ** 3 / 3.0 * len(ns)
+        tf_lauum = flops_lauum / (stage_ms["lauum"] * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
@@ -384,13 +388,15 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_eval * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (FP64 DMMA mainloop: Cholesky panel/trailing update, "
-                         "triangular inverse, W^T W)", "achieved": tf_all, "peak": dmma_peak, "unit": "TFLOP/s",
-                         "frac": tf_all / dmma_peak, "traffic": traffic,
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<CfgHalf,1,1,GeoLauum> (FP64 DMMA mainloop; the single "
+                         "largest launch of an evaluation: K^-1 = W^T W, lower tiles)", "achieved": tf_lauum,
+                         "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf_lauum / dmma_peak, "traffic": traffic,
+                         "flops_per_launch": flops_lauum, "launch_ms": stage_ms["lauum"],
                          "peak_source": "measured live: DMMA.8x8x4 register-operand probe (gpb_microbench); "
                                         "MEASURED_PEAKS.json has no FP64 entry; cuBLAS DGEMM 8192^3 = %.2f TFLOP/s"
                                         % cublas_dgemm,
-                         "flops_per_eval": flops_potrf + flops_inv},
+                         "all_gemm_launches": {"achieved": tf_all, "frac": tf_all / dmma_peak,
+                                               "flops_per_eval": flops_potrf + flops_inv}},
             "stages_ms": stage_ms,
             "cholesky": {"tflops": tf_potrf, "frac_of_fp64_tensor_peak": tf_potrf / dmma_peak,
                          "inverse_tflops": tf_inv, "inverse_frac": tf_inv / dmma_peak},

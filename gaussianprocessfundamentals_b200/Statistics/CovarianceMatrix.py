@@ -215,14 +215,37 @@ class SegmentedCovarianceMatrix(CovarianceMatrix):
     def _active(self) -> List[int]:
         return [i for i, blk in enumerate(self.data_input.data_inputs) if blk.n_train > 0]
 
+    def shard(self, group=None, rank=None, world=None):
+        """Distribute the non-empty blocks over the ranks of `group` (default: the world group) by estimated cost
+        (sharding.assign).  Afterwards every rank evaluates only its own blocks in `block_nll_and_grad` and the
+        per-block scalars and gradients are all-gathered, so the metric is identical on every rank and identical to
+        the single-process value (independent units, no data-path collective).  The per-block matrix
+        getters (get_L_K_blocks, ...) remain single-process."""
+        from ..sharding import Sharding, estimated_cost
+        self._need_data()
+        act = self._active()
+        costs = [estimated_cost(self.data_input.data_inputs[i].n_train) for i in act]
+        self._sharding = Sharding(costs, group=group, rank=rank, world=world)
+        self._blocks = None
+        return self._sharding
+
+    def _local_positions(self, act) -> List[int]:
+        """positions (into the active list) of the blocks this rank evaluates"""
+        sh = getattr(self, "_sharding", None)
+        return list(range(len(act))) if sh is None else list(sh.mine)
+
+    def _make_blocks(self, kernels, xs, ys):
+        return DeviceBlocks(kernels, xs, ys, want_grad=True)
+
     def _device_blocks(self) -> DeviceBlocks:
         self._need_data()
         if self._blocks is None:
             act = self._active()
+            act = [act[p] for p in self._local_positions(act)]
             kernels = [self.kernel.child_nodes[i] for i in act]
             xs = [self.data_input.data_inputs[i].data_x_train for i in act]
             ys = [self.data_input.data_inputs[i].get_detrended_y_train() for i in act]
-            self._blocks = DeviceBlocks(kernels, xs, ys, want_grad=True)
+            self._blocks = self._make_blocks(kernels, xs, ys) if act else None
         return self._blocks
 
     def block_nll_and_grad(self, hyper_parameter, noise, want_grad: bool = True):
@@ -230,15 +253,42 @@ class SegmentedCovarianceMatrix(CovarianceMatrix):
         w.r.t. the full hyper-parameter list (zeros for change points) and the noise"""
         blocks = self._device_blocks()
         act, sl = self._active(), self._slices()
+        sh = getattr(self, "_sharding", None)
         hp_lists = [list(hyper_parameter[sl[i]]) for i in act]
-        nll, grads = blocks.evaluate(hp_lists, [_noise_value(noise)] * len(act), want_grad)
+        glists = gnoise = None
+        if sh is None:
+            nll, grads = blocks.evaluate(hp_lists, [_noise_value(noise)] * len(act), want_grad)
+            if want_grad:
+                glists, gnoise = blocks.grads_as_lists(grads, hp_lists)
+        else:
+            # this rank's share, then one all-gather of (nll, info, flat gradient) per block
+            mine = sh.mine
+            if mine:
+                nll_l, grads_l = blocks.evaluate([hp_lists[p] for p in mine], [_noise_value(noise)] * len(mine),
+                                                 want_grad, check=False)
+                info_l = blocks.last[2]
+            else:
+                nll_l, grads_l, info_l = [], [], []
+            sizes = [sum(int(torch.as_tensor(h).numel()) for h in hp) + 1 for hp in hp_lists]
+            nll, grads, info = sh.combine(nll_l, grads_l if want_grad else None, info_l, sizes)
+            bad = np.nonzero(info)[0]
+            if bad.size:
+                raise engine.NotPositiveDefinite(int(info[bad[0]]))
+            if want_grad:
+                from ..program import unflatten_grad, compile_spec
+                scaled = bool(global_param.p_scaled_base_kernel)
+                glists, gnoise = [], []
+                for pos, i in enumerate(act):
+                    cn = self.kernel.child_nodes[i]
+                    entries = compile_spec(cn.to_spec(), cn.get_dimensionality(), scaled).entries
+                    glists.append(unflatten_grad(entries, grads[pos][:-1], like=hp_lists[pos]))
+                    gnoise.append(float(grads[pos][-1]))
         per_block = [None] * len(self.kernel.child_nodes)
         for pos, i in enumerate(act):
             per_block[i] = float(nll[pos])
             self.kernel.child_nodes[i]._remember(hp_lists[pos])
         if not want_grad:
             return per_block, None, None
-        glists, gnoise = blocks.grads_as_lists(grads, hp_lists)
         full = [torch.zeros_like(torch.as_tensor(h, dtype=torch.float64)) for h in hyper_parameter]
         for pos, i in enumerate(act):
             for off, g in enumerate(glists[pos]):

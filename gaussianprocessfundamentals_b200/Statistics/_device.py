@@ -32,14 +32,15 @@ class DeviceBlocks:
     def flat_hp(self, hp_lists: Sequence[list]) -> List[np.ndarray]:
         return [flatten_hp(p.compiled.entries, hp, p.n_hp) for p, hp in zip(self.programs, hp_lists)]
 
-    def evaluate(self, hp_lists: Sequence[list], noises: Sequence[float], grad: bool):
-        """assembly -> Cholesky -> NLL (-> inverse -> gradient); host buffers in and out (the end-to-end call)"""
+    def evaluate(self, hp_lists: Sequence[list], noises: Sequence[float], grad: bool, check: bool = True):
+        """assembly -> Cholesky -> NLL (-> inverse -> gradient); host buffers in and out (the end-to-end call).
+        check=False leaves the per-GP `info` in self.last for the caller (sharded evaluations raise on all ranks)."""
         stages = engine.STAGES_LML_GRAD if grad else engine.STAGES_LML
         nll, grads, info = self.plan.eval_host(self.flat_hp(hp_lists), [float(v) for v in noises], stages=stages)
         self.holds = "W" if grad else "L"
         self.last = (nll, grads, info)
         bad = np.nonzero(info)[0]
-        if bad.size:
+        if check and bad.size:
             raise engine.NotPositiveDefinite(int(info[bad[0]]))
         return nll, grads
 

@@ -275,7 +275,7 @@ int gpb_plan_buffer(const gpb_plan_t* p, int b, int which, void** ptr, size_t* b
 int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   if (!p) return fail_arg(1, "plan is null");
   if (!p->ws) return fail_arg(1, "plan is not bound");
-  if ((stages & (GPB_STAGE_INVERSE | GPB_STAGE_GRAD)) && !p->want_grad)
+  if ((stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI | GPB_STAGE_LAUUM | GPB_STAGE_GRAD)) && !p->want_grad)
     return fail_arg(2, "plan was created without gradient workspace");
   cudaStream_t s = (cudaStream_t)stream;
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
@@ -293,11 +293,11 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     CU(gpb::run_finalize(dm, p->B, log2pi, s), "finalize");
   }
   if (stages & GPB_STAGE_BACKSOLVE) CU(gpb::run_trsv(dm, p->B, p->n_max, 1, s), "backsolve");
-  if (stages & GPB_STAGE_INVERSE) {
+  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
     CU(gpb::run_trtri(dm, p->B, p->n_max, s), "trtri");
     CU(gpb::run_alpha(dm, p->B, p->n_max, s), "alpha");
-    CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
   }
+  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
   if (stages & GPB_STAGE_GRAD) CU(gpb::run_grad(dm, p->B, p->n_max, p->n_hp_max, p->n_ops_max, p->dim, s), "grad");
   return 0;
 }

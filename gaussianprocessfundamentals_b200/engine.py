@@ -13,6 +13,7 @@ from . import _lib
 from .program import CompiledProgram, compile_spec, flatten_hp, unflatten_grad
 
 STAGE_ASSEMBLE, STAGE_POTRF, STAGE_NLL, STAGE_INVERSE, STAGE_GRAD, STAGE_BACKSOLVE = 1, 2, 4, 8, 16, 32
+STAGE_TRTRI, STAGE_LAUUM = 64, 128   # the two halves of STAGE_INVERSE
 STAGES_LML, STAGES_LML_GRAD = 7, 31
 BUF_A, BUF_KINV, BUF_ALPHA, BUF_Z, BUF_X, BUF_Y, BUF_HP, BUF_NOISE, BUF_NLL, BUF_GRAD, BUF_INFO = range(11)
 

@@ -47,6 +47,8 @@ typedef struct gpb_plan gpb_plan_t;
 #define GPB_STAGE_INVERSE 8    /* W = L^-1, alpha = W^T z, Kinv = W^T W  */
 #define GPB_STAGE_GRAD 16      /* d nll / d theta, d nll / d s2           */
 #define GPB_STAGE_BACKSOLVE 32 /* alpha by substitution, L left intact    */
+#define GPB_STAGE_TRTRI 64     /* first half of INVERSE: W = L^-1, alpha  */
+#define GPB_STAGE_LAUUM 128    /* second half of INVERSE: Kinv = W^T W (one launch; bench.py's roofline kernel) */
 #define GPB_STAGES_LML 7
 #define GPB_STAGES_LML_GRAD 31
 
