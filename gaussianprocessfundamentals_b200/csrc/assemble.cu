@@ -26,10 +26,18 @@ struct AsmArgs {
   double* K; long long ld;
   int lower_only;
   const double* y; int aug;   // aug: row n receives y^T, (n,n) receives 0
+  int own_P, own_Q, own_p, own_q;   // distributed plans: write only the 128-blocks this process owns (own_P == 0: all)
 };
 
 __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, int T) {
   extern __shared__ __align__(16) unsigned char asm_smem[];
+  bool own_main = true, own_aug = a.aug && ti == T - 1;
+  if (a.own_P) {
+    constexpr int R = GPB_NB / A_T;
+    own_main = ((ti / R) % a.own_P == a.own_p) && ((tj / R) % a.own_Q == a.own_q);
+    own_aug = own_aug && ((int)(a.n / GPB_NB) % a.own_P == a.own_p) && ((tj / R) % a.own_Q == a.own_q);
+    if (!own_main && !own_aug) return;
+  }
   int32_t* s_code = reinterpret_cast<int32_t*>(asm_smem);
   double* s_hp = reinterpret_cast<double*>(asm_smem + ((a.n_ops * GPB_OP_WORDS * 4 + 15) / 16) * 16);
   double* s_xi = s_hp + ((a.n_hp + 1) / 2) * 2 + 2;
@@ -50,7 +58,7 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   const long long gi = i0 + r;
   GpbPair p;
   p.xi = s_xi + r * a.dim; p.dim = a.dim; p.hp = s_hp; p.cp_mode = a.cp_mode; p.gi = gi;
-  if (gi < a.n) {
+  if (gi < a.n && own_main) {
 #pragma unroll 1
     for (int q = 0; q < A_T / 4; ++q) {
       const int c = cg + 4 * q;
@@ -63,13 +71,17 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
       a.K[gi + gj * a.ld] = v;
     }
   }
-  if (a.aug && ti == T - 1) {
+  if (own_aug) {
     // carried right-hand side: row n of the factorisation workspace
     if (tid < A_T) {
       const long long gj = j0 + tid;
       if (gj < a.n) a.K[a.n + gj * a.ld] = a.y[gj];
     }
-    if (tj == T - 1 && tid == 0) a.K[a.n + a.n * a.ld] = 0.0;
+  }
+  if (a.aug && ti == T - 1 && tj == T - 1 && tid == 0) {
+    // element (n, n) accumulates -z^T z; in a distributed plan it belongs to block (n / 128, n / 128)
+    const int bn = (int)(a.n / GPB_NB);
+    if (!a.own_P || (bn % a.own_P == a.own_p && bn % a.own_Q == a.own_q)) a.K[a.n + a.n * a.ld] = 0.0;
   }
 }
 
@@ -82,6 +94,7 @@ __global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __r
   a.code = d.code; a.n_ops = d.n_ops; a.dim = d.dim; a.cp_mode = d.cp_mode;
   a.X = d.X; a.X2 = nullptr; a.n = d.n; a.m = d.n; a.hp = d.hp; a.n_hp = d.n_hp; a.noise = d.noise;
   a.K = d.A; a.ld = d.ld; a.lower_only = 1; a.y = d.y; a.aug = d.aug;
+  a.own_P = d.own_P; a.own_Q = d.own_Q; a.own_p = d.own_p; a.own_q = d.own_q;
   assemble_tile(a, ti, tj, T);
 }
 
@@ -226,6 +239,7 @@ cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int c
   a.code = code_dev; a.n_ops = n_ops; a.dim = dim; a.cp_mode = cp_mode;
   a.X = X; a.X2 = X2; a.n = n; a.m = m; a.hp = hp_dev; a.n_hp = n_hp; a.noise = noise_dev;
   a.K = K; a.ld = ldk; a.lower_only = lower_only; a.y = nullptr; a.aug = 0;
+  a.own_P = a.own_Q = a.own_p = a.own_q = 0;
   const int Tm = (int)((n + A_T - 1) / A_T), Tn = (int)((m + A_T - 1) / A_T);
   if (Tm == 0 || Tn == 0) return cudaSuccess;
   const size_t smem = asm_smem_bytes(n_ops, n_hp, dim);

@@ -4,8 +4,8 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "linalg.cu", "assemble.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "program.cuh", "internal.h", os.path.join("..", "..", "include", "gpb.h")]
+SOURCES = ["capi.cu", "linalg.cu", "assemble.cu", "dist.cu"]
+HEADERS = ["common.cuh", "gemm.cuh", "program.cuh", "internal.h", "dist.h", os.path.join("..", "..", "include", "gpb.h")]
 OUT = os.path.join(HERE, "libgpb.so")
 
 NVCC_FLAGS = [
@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

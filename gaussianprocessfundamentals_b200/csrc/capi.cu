@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/gpb.h"
+#include "dist.h"
 #include "internal.h"
 #include "program.cuh"
 
@@ -61,6 +62,13 @@ struct gpb_plan {
   bool own_streams;
   char* h_in;   // pinned mirror of the small input region
   char* h_out;  // pinned mirror of the small output region
+  gpb::DistCtx* dist;       // non-null: ONE GP factorised over a process grid (dist.cu)
+  size_t off_stage[2];      // panel staging buffers of a distributed plan
+  GpbMat h_desc0;           // host copy of the first descriptor (distributed plans)
+};
+
+struct gpb_dist {
+  gpb::DistCtx* ctx;
 };
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -143,7 +151,8 @@ int gpb_assemble(const gpb_program_t* prog, const double* X, const double* X2, i
   return 0;
 }
 
-int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb_plan_t** out) {
+static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb::DistCtx* dist,
+                       gpb_plan_t** out) {
   if (B <= 0) return fail_arg(1, "B <= 0");
   if (!progs) return fail_arg(2, "progs is null");
   if (!n) return fail_arg(3, "n is null");
@@ -151,7 +160,8 @@ int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, 
   int rc = ensure_init();
   if (rc) return rc;
   gpb_plan* p = new gpb_plan;
-  p->B = B; p->want_grad = want_grad ? 1 : 0; p->ws = nullptr;
+  p->B = B; p->want_grad = want_grad ? 1 : 0; p->ws = nullptr; p->dist = dist;
+  p->off_stage[0] = p->off_stage[1] = 0;
   p->n_max = 0; p->n_hp_max = 0; p->n_ops_max = 0; p->dim = progs[0] ? progs[0]->dim : 1;
   p->mats.resize(B); p->progs.assign(progs, progs + B);
   p->hp_prefix.resize(B + 1); p->grad_prefix.resize(B + 1);
@@ -202,6 +212,9 @@ int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, 
     m.off[GPB_BUF_GRAD] = p->off_grad_all + p->grad_prefix[b] * 8; m.bytes[GPB_BUF_GRAD] = (size_t)(g->n_hp + 1) * 8;
     m.off[GPB_BUF_INFO] = p->off_info_all + (size_t)b * 4; m.bytes[GPB_BUF_INFO] = 4;
   }
+  if (dist) {
+    for (int i = 0; i < 2; ++i) { p->off_stage[i] = off; off = al(off + gpb::dist_stage_bytes((int)n[0])); }
+  }
   p->ws_bytes = off;
   p->h_in = nullptr; p->h_out = nullptr;
   cudaError_t e = cudaMallocHost(&p->h_in, p->in_bytes + 16);
@@ -221,6 +234,18 @@ int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, 
   p->own_streams = true;
   *out = p;
   return 0;
+}
+
+int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb_plan_t** out) {
+  return plan_create(B, progs, n, want_grad, nullptr, out);
+}
+
+int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out) {
+  if (!prog) return fail_arg(1, "program is null");
+  if (!dist || !dist->ctx) return fail_arg(4, "dist is null");
+  if (want_grad) return fail_arg(3, "distributed plans evaluate the likelihood only (stages ASSEMBLE | POTRF | NLL)");
+  const gpb_program_t* progs[1] = {prog};
+  return plan_create(1, progs, &n, 0, dist->ctx, out);
 }
 
 size_t gpb_plan_workspace_bytes(const gpb_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
@@ -254,7 +279,9 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     d.info = (int*)(w + m.off[GPB_BUF_INFO]);
     d.n = (int)m.n; d.ld = m.ld; d.dim = g->dim; d.n_ops = g->n_ops; d.n_hp = g->n_hp; d.aug = 1;
     d.cp_mode = g->cp_mode; d.n_gtiles = m.n_gtiles;
+    if (p->dist) { d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q; }
   }
+  p->h_desc0 = h[0];
   CU(cudaMemcpy(p->ws + p->off_desc, h.data(), (size_t)p->B * sizeof(GpbMat), cudaMemcpyHostToDevice), "gpb_plan_bind");
   CU(cudaMemset(p->ws + p->off_out, 0, p->out_bytes), "gpb_plan_bind");
   return 0;
@@ -280,6 +307,24 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
   p->ex.main = s;
+  if (p->dist) {
+    if (stages & ~(GPB_STAGE_ASSEMBLE | GPB_STAGE_POTRF | GPB_STAGE_NLL))
+      return fail_arg(2, "distributed plans support the stages ASSEMBLE | POTRF | NLL");
+    if (stages & GPB_STAGE_ASSEMBLE) {
+      CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
+      CU(gpb::run_assemble_batched(dm, 1, p->n_max, s), "assemble");
+    }
+    if (stages & GPB_STAGE_POTRF) {
+      double* stage[2] = {(double*)(p->ws + p->off_stage[0]), (double*)(p->ws + p->off_stage[1])};
+      cudaError_t e = gpb::run_potrf_dist(dm, p->h_desc0, *p->dist, stage, p->ex);
+      if (e != cudaSuccess) {
+        if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }
+        return fail_cuda(e, "potrf_dist");
+      }
+    }
+    if (stages & GPB_STAGE_NLL) CU(gpb::run_finalize_dist(dm, std::log(M_PI * 2.0), s), "finalize_dist");
+    return 0;
+  }
   if (stages & GPB_STAGE_ASSEMBLE) {
     CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, (size_t)p->B * 4, s), "reset info");
     CU(gpb::run_assemble_batched(dm, p->B, p->n_max, s), "assemble");
@@ -343,6 +388,47 @@ void gpb_plan_destroy(gpb_plan_t* p) {
   if (p->h_in) cudaFreeHost(p->h_in);
   if (p->h_out) cudaFreeHost(p->h_out);
   delete p;
+}
+
+/* ---- process grid of the distributed factorisation ---------------------------------------------------------- */
+int gpb_dist_unique_id(unsigned char* id128) {
+  if (!id128) return fail_arg(1, "id is null");
+  if (gpb::dist_unique_id(id128)) { g_err = gpb::dist_last_error(); return 2000; }
+  return 0;
+}
+
+int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q, gpb_dist_t** out) {
+  if (!id128) return fail_arg(1, "id is null");
+  if (world < 1 || rank < 0 || rank >= world) return fail_arg(2, "rank / world out of range");
+  if (P < 1 || Q < 1 || P * Q != world || P > GPB_DIST_MAX_P) return fail_arg(4, "P x Q must equal world, P <= 8");
+  if (!out) return fail_arg(6, "out is null");
+  int rc = ensure_init();
+  if (rc) return rc;
+  gpb::DistCtx* ctx = nullptr;
+  if (gpb::dist_create(id128, rank, world, P, Q, &ctx)) { g_err = gpb::dist_last_error(); return 2000; }
+  gpb_dist* d = new gpb_dist;
+  d->ctx = ctx;
+  *out = d;
+  return 0;
+}
+
+void gpb_dist_destroy(gpb_dist_t* d) {
+  if (!d) return;
+  gpb::dist_destroy(d->ctx);
+  delete d;
+}
+
+int gpb_dist_owner(int I, int J, int P, int Q) {
+  if (I < 0 || J < 0 || P < 1 || Q < 1) return -1;
+  return (I % P) * Q + (J % Q);
+}
+
+int gpb_dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first) {
+  if (k < 0 || n_tiles < 0) return fail_arg(1, "k / n_tiles negative");
+  if (P < 1 || P > GPB_DIST_MAX_P) return fail_arg(3, "P out of range");
+  if (!seg_base || !seg_count || !seg_first) return fail_arg(4, "null output");
+  gpb::dist_panel_segments(k, n_tiles, P, seg_base, seg_count, seg_first);
+  return 0;
 }
 
 int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double* B, int ldb, double* C, int ldc,

@@ -25,6 +25,8 @@ struct GpbMat {
   double* grad;      // [n_hp+1] out (last entry: d nll / d s2)
   int* info;         // device scalar out: 0 ok, j>0 first non-positive pivot (1-based)
   int n, ld, dim, n_ops, n_hp, aug, cp_mode, n_gtiles;
+  // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, J mod own_Q); own_P == 0: all
+  int own_P, own_Q, own_p, own_q;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {

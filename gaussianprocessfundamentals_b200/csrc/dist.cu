@@ -1,0 +1,385 @@
+// Distributed Cholesky / LML of ONE large GP over a P x Q process grid (one process per GPU, NCCL over NVLink).
+//
+// Replaces, for matrices too large or too slow for one GPU, the same reference calls as the single-GPU plan:
+// HolisticCovarianceMatrix.get_L_K / get_L_alpha (Statistics/CovarianceMatrix.py:247-265) and
+// LogLikelihood.get_metric (Metrics/LogLikelihood.py:30-65).  BASELINE config 5 / SURVEY 8(e), second row.
+//
+// Layout: 2D block-cyclic OWNERSHIP of the 128 x 128 blocks of the lower triangle - block (I, J) is assembled and
+// updated by rank (I mod P) * Q + (J mod Q) - over REPLICATED storage: every rank holds the full (n+1) x ld
+// column-major workspace of the single-GPU plan, its own blocks are live, and each finished panel (block column k of L)
+// is broadcast to all ranks, so that after the factorisation every rank holds the complete L (the later stages -
+// triangular solves, inverse, gradient - read all of it).  The exchange per step k is
+//   P == 1 : one ncclBroadcast of the packed panel (diagonal block + all blocks below it) from the column's owner
+//   P  > 1 : ncclBroadcast of {L_kk, inv(L_kk)} from the diagonal owner, then one grouped ncclBroadcast per process
+//            row of the panel blocks that row owns.
+// NVSwitch gives every pair of GPUs full bandwidth, so replicating the panel (n^2/2 doubles per rank over the whole
+// factorisation, 17 GB at n = 65536, ~25 ms at the measured 700 GB/s) is cheaper than the bookkeeping of row/column
+// communicators; the grid shape only balances the load.  Panels travel tile-major through two staging buffers.
+//
+// Streams: the critical path (diagonal block, panel, exchange, update of the next block column) runs on the plan's
+// high-priority stream, the bulk of the trailing update on the low-priority one (look-ahead), exactly as on one GPU.
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "dist.h"
+#include "gemm.cuh"
+#include "internal.h"
+
+namespace gpb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (no link-time dependency: single-GPU users never load it).  Minimal declarations of the
+// stable NCCL 2 C API; `ncclFloat64` = 8 and `ncclSum` = 0 in every NCCL 2 release.
+// ---------------------------------------------------------------------------------------------------------------
+typedef int ncclResult_t;
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(NcclId*) = nullptr;
+  ncclResult_t (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(void*) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::string g_dist_err;
+const char* dist_last_error() { return g_dist_err.c_str(); }
+
+static bool nccl_load() {
+  if (g_nccl.handle) return true;
+  // prefer the copy already mapped into the process (torch's bundled libnccl), then the system one
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { g_dist_err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+  NcclApi a;
+  a.handle = h;
+#define GPB_SYM(field, name) *(void**)(&a.field) = dlsym(h, name); if (!a.field) { g_dist_err = "libnccl lacks " name; return false; }
+  GPB_SYM(GetUniqueId, "ncclGetUniqueId")
+  GPB_SYM(CommInitRank, "ncclCommInitRank")
+  GPB_SYM(CommDestroy, "ncclCommDestroy")
+  GPB_SYM(Broadcast, "ncclBroadcast")
+  GPB_SYM(AllReduce, "ncclAllReduce")
+  GPB_SYM(GroupStart, "ncclGroupStart")
+  GPB_SYM(GroupEnd, "ncclGroupEnd")
+  GPB_SYM(GetErrorString, "ncclGetErrorString")
+#undef GPB_SYM
+  g_nccl = a;
+  return true;
+}
+static bool nccl_ok(ncclResult_t r, const char* where) {
+  if (r == 0) return true;
+  g_dist_err = std::string(where) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+  return false;
+}
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0;
+
+int dist_unique_id(unsigned char* id128) {
+  if (!nccl_load()) return 1;
+  NcclId id;
+  if (!nccl_ok(g_nccl.GetUniqueId(&id), "ncclGetUniqueId")) return 1;
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, DistCtx** out) {
+  if (!nccl_load()) return 1;
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  if (!nccl_ok(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank")) return 1;
+  DistCtx* d = new DistCtx;
+  d->comm = comm; d->rank = rank; d->world = world; d->P = P; d->Q = Q; d->p = rank / Q; d->q = rank % Q;
+  *out = d;
+  return 0;
+}
+
+void dist_destroy(DistCtx* d) {
+  if (!d) return;
+  if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+  delete d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side ownership arithmetic (also exported through the C-ABI for the CPU tests)
+// ---------------------------------------------------------------------------------------------------------------
+void dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first) {
+  // tile t of panel k is block row I = k + t; it belongs to process row I mod P.  Staging order: by process row, each
+  // row's tiles ascending.
+  int base = 0;
+  for (int o = 0; o < P; ++o) {
+    const int t0 = ((o - k) % P + P) % P;          // first tile of process row o
+    const int cnt = t0 < n_tiles ? (n_tiles - t0 + P - 1) / P : 0;
+    seg_base[o] = base; seg_count[o] = cnt; seg_first[o] = t0;
+    base += cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------------------------
+struct PanelMap {
+  int P;
+  int seg_base[GPB_DIST_MAX_P];
+  int seg_first[GPB_DIST_MAX_P];
+  __device__ __forceinline__ int slot(int k, int t) const {
+    const int o = (k + t) % P;
+    return seg_base[o] + (t - seg_first[o]) / P;
+  }
+};
+
+constexpr int TILE_ELEMS = GPB_NB * GPB_NB;
+
+// A -> stage for the panel tiles this rank owns (mode 0), stage -> A for the tiles it does not own (mode 1).
+// Tile t = block row k + t of block column k; t0 = first tile handled (0 includes the diagonal block).
+__global__ void __launch_bounds__(256) panel_copy_kernel(double* __restrict__ A, long long ld, int nrows, int k, int t0,
+                                                         double* __restrict__ stage, PanelMap map, int my_p, int owner_col,
+                                                         int my_q, int mode) {
+  const int t = t0 + blockIdx.x;
+  const int I = k + t;
+  const bool mine = (I % map.P == my_p) && (my_q == owner_col);
+  if ((mode == 0) != mine) return;
+  double* st = stage + (size_t)map.slot(k, t) * TILE_ELEMS;
+  const int rows = min(GPB_NB, nrows - I * GPB_NB);
+  const int cols = min(GPB_NB, nrows - k * GPB_NB);
+  double* a = A + (size_t)I * GPB_NB + (size_t)k * GPB_NB * ld;
+  for (int idx = threadIdx.x; idx < TILE_ELEMS; idx += 256) {
+    const int i = idx & (GPB_NB - 1), c = idx >> 7;
+    if (i < rows && c < cols) {
+      if (mode == 0) st[idx] = a[i + (size_t)c * ld];
+      else a[i + (size_t)c * ld] = st[idx];
+    } else if (mode == 0) {
+      st[idx] = 0.0;
+    }
+  }
+}
+
+// plain copy of 128 x 128 doubles (inverse of the diagonal block in / out of the staging buffer)
+__global__ void __launch_bounds__(256) tile_copy_kernel(double* __restrict__ dst, const double* __restrict__ src) {
+  for (int idx = threadIdx.x + blockIdx.x * 256; idx < TILE_ELEMS; idx += 256 * gridDim.x) dst[idx] = src[idx];
+}
+
+// panel product for the blocks of block column k owned by this process row: A[I, k] = A[I, k] * Wd_k^T
+struct GeoDistPanel {
+  const GpbMat* mats;
+  int k, P, p;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
+    static_assert(BN == GPB_NB, "the in-place panel product needs full-width tiles");
+    const GpbMat& d = mats[0];
+    const int nrows = d.n + d.aug;
+    const int i0 = (k + 1) * GPB_NB + blockIdx.x * BM;
+    if (i0 >= nrows) return false;
+    if ((i0 / GPB_NB) % P != p) return false;
+    double* Pn = d.A + (size_t)k * GPB_NB * d.ld + i0;
+    J.A = Pn; J.C = Pn;
+    J.B = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+    J.lda = J.ldc = d.ld; J.ldb = GPB_NB;
+    J.mrem = min(BM, nrows - i0);
+    J.nrem = GPB_NB;
+    J.klo = 0; J.khi = GPB_NB;
+    J.alpha = 1.0; J.beta = 0.0;
+    return true;
+  }
+};
+
+// trailing update with panel k of the blocks (I, J) this rank owns, J in [J_lo, J_hi):  A[I, J] -= L[I, k] L[J, k]^T.
+// grid.y enumerates this rank's block columns of the range, grid.x the BM-row tiles from the diagonal block down.
+struct GeoDistSyrk {
+  const GpbMat* mats;
+  int k, J_lo, J_hi, P, Q, p, q;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J) const {
+    static_assert(BN == GPB_NB, "block columns are 128 wide");
+    const GpbMat& d = mats[0];
+    const int nrows = d.n + d.aug;
+    const int Jf = J_lo + ((q - J_lo) % Q + Q) % Q;     // first block column >= J_lo owned by process column q
+    const int Jb = Jf + (int)blockIdx.y * Q;
+    if (Jb >= J_hi) return false;
+    const int row = Jb * GPB_NB + (int)blockIdx.x * BM;
+    if (row >= nrows) return false;
+    if ((row / GPB_NB) % P != p) return false;
+    const size_t ld = d.ld;
+    const double* Pn = d.A + (size_t)k * GPB_NB * ld;
+    J.A = Pn + row;
+    J.B = Pn + (size_t)Jb * GPB_NB;
+    J.C = d.A + row + (size_t)Jb * GPB_NB * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(BM, nrows - row);
+    J.nrem = min(BN, nrows - Jb * GPB_NB);
+    J.klo = 0; J.khi = GPB_NB;
+    J.alpha = -1.0; J.beta = 1.0;
+    return true;
+  }
+};
+
+// nll from the replicated factor: sum(log diag L), z^T z from the carried row, first non-positive / NaN pivot
+__global__ void __launch_bounds__(1024) dist_finalize_kernel(const GpbMat* __restrict__ mats, double log2pi) {
+  __shared__ double s_ld[32], s_q[32];
+  __shared__ int s_bad[32];
+  const GpbMat d = mats[0];
+  const int n = d.n;
+  const size_t ld = d.ld;
+  double lsum = 0.0, qsum = 0.0;
+  int bad = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double lii = d.A[i + (size_t)i * ld];
+    const double z = d.A[n + (size_t)i * ld];
+    d.zvec[i] = z;
+    if (!(lii > 0.0)) bad = min(bad, i + 1);
+    lsum += log(lii);
+    qsum += z * z;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  lsum = warp_sum(lsum); qsum = warp_sum(qsum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+  if (lane == 0) { s_ld[warp] = lsum; s_q[warp] = qsum; s_bad[warp] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    int w = 0x7fffffff;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_ld[i]; b += s_q[i]; w = min(w, s_bad[i]); }
+    const int info = (w == 0x7fffffff) ? 0 : w;
+    *d.info = info;
+    *d.nll = info ? nan("") : 0.5 * b + a + 0.5 * ((double)n * log2pi);
+  }
+}
+
+#define GPB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+#define GPB_NK(x, where) do { if (!nccl_ok((x), where)) return cudaErrorUnknown; } while (0)
+
+template <class Cfg, class Geo>
+static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s) {
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPB_CK(cudaFuncSetAttribute(gemm_kernel<Cfg, false, false, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_kernel<Cfg, false, false, Geo><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+static int count_owned_cols(int J_lo, int J_hi, int Q, int q) {
+  if (J_hi <= J_lo) return 0;
+  const int Jf = J_lo + ((q - J_lo) % Q + Q) % Q;
+  return Jf < J_hi ? (J_hi - Jf + Q - 1) / Q : 0;
+}
+
+size_t dist_stage_bytes(int n) {
+  const int nrows = n + 1;
+  const int nt = (nrows + GPB_NB - 1) / GPB_NB;
+  return (size_t)(nt + 2) * TILE_ELEMS * sizeof(double);    // +1 slot for inv(L_kk), +1 spare
+}
+
+// The distributed factorisation.  dm: device descriptor (one GpbMat), h: its host copy, stage[2]: staging buffers of
+// dist_stage_bytes(n) each.
+cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex) {
+  using Cfg = CfgHalf;
+  constexpr int BM = Cfg::BM;
+  const int n = h.n, nrows = h.n + h.aug;
+  const int nblk = (n + GPB_NB - 1) / GPB_NB;              // pivot block columns
+  const int nbr = (nrows + GPB_NB - 1) / GPB_NB;           // block rows (the carried y row may add one)
+  const int P = D.P, Q = D.Q, p = D.p, q = D.q;
+  cudaStream_t cs = ex.crit, ss = ex.side;
+  GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
+  GPB_CK(cudaStreamWaitEvent(cs, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
+  const size_t ld = h.ld;
+  for (int k = 0; k < nblk; ++k) {
+    const int qk = k % Q, pk = k % P;
+    const int diag_owner = pk * Q + qk;
+    const bool full = (k + 1) * GPB_NB <= n;               // full pivot block: a panel exists below it
+    const int nt = full ? nbr - k : 1;                     // tiles of the panel incl. the diagonal block
+    double* st = stage[k & 1];
+    PanelMap map;
+    map.P = P;
+    int seg_base[GPB_DIST_MAX_P], seg_count[GPB_DIST_MAX_P], seg_first[GPB_DIST_MAX_P];
+    dist_panel_segments(k, nt, P, seg_base, seg_count, seg_first);
+    for (int o = 0; o < P; ++o) { map.seg_base[o] = seg_base[o]; map.seg_first[o] = seg_first[o]; }
+    double* st_wd = st + (size_t)nt * TILE_ELEMS;          // slot of inv(L_kk) behind the panel tiles
+    double* Wk = h.Wd + (size_t)k * TILE_ELEMS;
+
+    // ---- diagonal block (its owner), then the panel blocks (their owners in process column qk) ----------------
+    if (D.rank == diag_owner) GPB_CK(run_diag(dm, 1, k, cs));
+    if (P > 1 && full) {
+      // the other process rows of column qk need inv(L_kk) for their panel blocks: ship {L_kk, inv(L_kk)} first
+      if (D.rank == diag_owner) {
+        panel_copy_kernel<<<1, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, 0, st, map, p, qk, q, 0);
+        tile_copy_kernel<<<8, 256, 0, cs>>>(st_wd, Wk);
+        g_launches += 2;
+      }
+      GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
+      GPB_NK(g_nccl.Broadcast(st + (size_t)map.seg_base[pk] * TILE_ELEMS, st + (size_t)map.seg_base[pk] * TILE_ELEMS,
+                              TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(diag)");
+      GPB_NK(g_nccl.Broadcast(st_wd, st_wd, TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(inv diag)");
+      GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+      if (D.rank != diag_owner) {
+        panel_copy_kernel<<<1, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, 0, st, map, p, qk, q, 1);
+        tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd);
+        g_launches += 2;
+      }
+    }
+    if (full && q == qk) {
+      const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
+      GPB_CK((launch_geo<Cfg>(GeoDistPanel{dm, k, P, p}, dim3(Tm, 1, 1), cs)));
+    }
+    // ---- exchange: pack own tiles, broadcast every process row's segment, unpack the others' tiles ------------
+    const int t0 = (P > 1 && full) ? 1 : 0;                // the diagonal tile already travelled when P > 1
+    if (nt - t0 > 0) {
+      if (q == qk) {
+        panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 0);
+        ++g_launches;
+      }
+      GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
+      for (int o = 0; o < P; ++o) {
+        int first = seg_base[o], cnt = seg_count[o];
+        if (t0 == 1 && o == pk) { first += 1; cnt -= 1; }  // skip the diagonal tile (slot 0 of its owner's segment)
+        if (cnt <= 0) continue;
+        double* b = st + (size_t)first * TILE_ELEMS;
+        GPB_NK(g_nccl.Broadcast(b, b, (size_t)cnt * TILE_ELEMS, NCCL_F64, o * Q + qk, D.comm, cs), "ncclBroadcast(panel)");
+      }
+      GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+      panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 1);
+      ++g_launches;
+    }
+    if (!full) continue;
+    GPB_CK(cudaEventRecord(ex.ev_e[k & 1], cs));
+    // ---- trailing update: block column k+1 on the critical stream, k+2 first and then the rest on the side stream
+    const int J1 = k + 1, Jend = nbr;
+    auto syrk = [&](int Jlo, int Jhi, cudaStream_t s) -> cudaError_t {
+      if (Jhi > Jend) Jhi = Jend;
+      const int nc = count_owned_cols(Jlo, Jhi, Q, q);
+      if (nc == 0) return cudaSuccess;
+      const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
+      return launch_geo<Cfg>(GeoDistSyrk{dm, k, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s);
+    };
+    if (k > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(k - 1) & 1], 0));
+    GPB_CK(syrk(J1, J1 + 1, cs));
+    GPB_CK(cudaStreamWaitEvent(ss, ex.ev_e[k & 1], 0));
+    GPB_CK(syrk(J1 + 1, J1 + 2, ss));
+    GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ss));
+    GPB_CK(syrk(J1 + 2, Jend, ss));
+  }
+  GPB_CK(cudaEventRecord(ex.ev_join[0], cs));
+  GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  return cudaSuccess;
+}
+
+cudaError_t run_finalize_dist(const GpbMat* dm, double log2pi, cudaStream_t s) {
+  dist_finalize_kernel<<<1, 1024, 0, s>>>(dm, log2pi);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+}  // namespace gpb

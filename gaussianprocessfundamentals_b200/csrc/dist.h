@@ -1,0 +1,25 @@
+// Process-grid context of the distributed (multi-GPU) factorisation; see dist.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "internal.h"
+
+#define GPB_DIST_MAX_P 8
+
+namespace gpb {
+
+struct DistCtx {
+  void* comm;                 // ncclComm_t
+  int rank, world, P, Q, p, q;  // rank = p * Q + q
+};
+
+const char* dist_last_error();
+int dist_unique_id(unsigned char* id128);
+int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, DistCtx** out);
+void dist_destroy(DistCtx* d);
+void dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
+size_t dist_stage_bytes(int n);
+cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex);
+cudaError_t run_finalize_dist(const GpbMat* dm, double log2pi, cudaStream_t s);
+
+}  // namespace gpb

@@ -21,6 +21,7 @@ struct Exec {
 
 // ---- linalg.cu ------------------------------------------------------------------------------------------------
 cudaError_t run_potrf(const GpbMat* dmats, int B, int n_max, int aug, bool lookahead, const Exec& ex);
+cudaError_t run_diag(const GpbMat* dmats, int B, int k, cudaStream_t s);   // diagonal block k: Cholesky + inverse
 cudaError_t run_finalize(const GpbMat* dmats, int B, double log2pi, cudaStream_t s);
 cudaError_t run_trtri(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
 cudaError_t run_alpha(const GpbMat* dmats, int B, int n_max, cudaStream_t s);

@@ -565,6 +565,12 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
                     : potrf_impl<CfgBig>(dm, B, n_max, aug, lookahead, ex);
 }
 
+cudaError_t run_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
+  diag_kernel<<<B, 256, D_SMEM_BYTES, s>>>(dm, k);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
 cudaError_t run_finalize(const GpbMat* dm, int B, double log2pi, cudaStream_t s) {
   finalize_kernel<<<B, 256, 0, s>>>(dm, log2pi);
   ++g_launches;

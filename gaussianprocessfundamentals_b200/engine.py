@@ -96,7 +96,9 @@ class Plan:
     """B independent GPs evaluated together: assembly -> Cholesky (+ carried y) -> NLL -> inverse -> gradient."""
 
     def __init__(self, programs: Sequence[DeviceProgram], ns: Sequence[int], want_grad: bool = True,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, grid: Optional["ProcessGrid"] = None):
+        """grid: a ProcessGrid makes this the distributed plan of ONE GP (2D block-cyclic block ownership, NCCL panel
+        broadcasts; likelihood stages only).  Every rank of the grid must construct it and call eval collectively."""
         require_cuda()
         lib = _lib.load()
         self.lib = lib
@@ -109,7 +111,15 @@ class Plan:
         handles = (ctypes.c_void_p * self.B)(*[p.handle for p in self.programs])
         n_arr = (ctypes.c_int64 * self.B)(*self.ns)
         h = ctypes.c_void_p()
-        _lib.check(lib.gpb_plan_create(self.B, handles, n_arr, 1 if want_grad else 0, ctypes.byref(h)), "gpb_plan_create")
+        self.grid = grid
+        if grid is not None:
+            if self.B != 1 or want_grad:
+                raise _lib.GpbError("a distributed plan holds one GP and evaluates the likelihood only")
+            _lib.check(lib.gpb_plan_create_dist(self.programs[0].handle, self.ns[0], 0, grid.handle, ctypes.byref(h)),
+                       "gpb_plan_create_dist")
+        else:
+            _lib.check(lib.gpb_plan_create(self.B, handles, n_arr, 1 if want_grad else 0, ctypes.byref(h)),
+                       "gpb_plan_create")
         self.handle = h
         self.ws_bytes = int(lib.gpb_plan_workspace_bytes(h))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
@@ -195,6 +205,51 @@ class Plan:
         try:
             if getattr(self, "handle", None) is not None and _lib._lib is not None:
                 _lib._lib.gpb_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class ProcessGrid:
+    """P x Q grid of the processes of a torch.distributed group (one process per GPU) with its own NCCL communicator
+    inside libgpb (gpb_dist_init).  rank = p * Q + q.  torch.distributed is used once, to ship the NCCL unique id."""
+
+    def __init__(self, P: int, Q: int, group=None):
+        import torch.distributed as dist
+        require_cuda()
+        lib = _lib.load()
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _lib.GpbError("ProcessGrid needs an initialised torch.distributed process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if P * Q != self.world:
+            raise ValueError("P x Q = %d x %d does not match the group size %d" % (P, Q, self.world))
+        self.P, self.Q, self.p, self.q = int(P), int(Q), self.rank // Q, self.rank % Q
+        ident = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.check(lib.gpb_dist_unique_id(ident), "gpb_dist_unique_id")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+        h = ctypes.c_void_p()
+        _lib.check(lib.gpb_dist_init(ident, self.rank, self.world, self.P, self.Q, ctypes.byref(h)), "gpb_dist_init")
+        self.handle = h
+
+    @staticmethod
+    def default_shape(world: int):
+        """(P, Q) with P <= Q, P a power of two: 1x1, 1x2, 2x2, 2x4 (the NVSwitch fabric is uniform, so the shape only
+        balances the load; P = 1 saves the diagonal-block round trip of every step)"""
+        P = 1
+        while (P * 2) * (P * 2) <= world and world % (P * 2) == 0:
+            P *= 2
+        return P, world // P
+
+    def owner(self, I: int, J: int) -> int:
+        return (I % self.P) * self.Q + (J % self.Q)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and _lib._lib is not None:
+                _lib._lib.gpb_dist_destroy(self.handle)
+                self.handle = None
         except Exception:
             pass
 

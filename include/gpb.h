@@ -25,6 +25,7 @@ extern "C" {
 
 typedef struct gpb_program gpb_program_t;
 typedef struct gpb_plan gpb_plan_t;
+typedef struct gpb_dist gpb_dist_t;
 
 /* op codes of the postfix kernel program, 4 int32 words per op {op, a, b, c}; see csrc/program.cuh */
 #define GPB_SE 1
@@ -109,6 +110,27 @@ int gpb_plan_eval_host(gpb_plan_t* plan, int stages, const double* const* X_host
                        const double* const* hp_host, const double* noise_host, double* nll_host, double* grad_host,
                        int* info_host, void* stream);
 void gpb_plan_destroy(gpb_plan_t* plan);
+
+/* ---- one large GP over a process grid (one process per GPU; NCCL over NVLink / NVSwitch) --------------------
+ * Replaces the same reference calls as a B = 1 plan (HolisticCovarianceMatrix.get_L_K / get_L_alpha,
+ * Statistics/CovarianceMatrix.py:247-265; LogLikelihood.get_metric, Metrics/LogLikelihood.py:30-65) when one matrix
+ * is factorised by several GPUs: the 128 x 128 blocks of the lower triangle are owned 2D block-cyclically, block (I, J)
+ * by rank (I mod P) * Q + (J mod Q); every finished panel is broadcast (ncclBroadcast), so all ranks end up with the
+ * complete factor L, z = L^-1 y and the same nll / info.  libnccl.so.2 is bound at run time by gpb_dist_unique_id /
+ * gpb_dist_init only.
+ *   rank 0 calls gpb_dist_unique_id and ships the 128 bytes to the other ranks with the host's own transport;
+ *   every rank then calls gpb_dist_init (collective), creates the plan with gpb_plan_create_dist, binds a workspace,
+ *   fills the SAME X / y / hp / noise into the plan's buffers and calls gpb_plan_eval / gpb_plan_eval_host with
+ *   stages from ASSEMBLE | POTRF | NLL (collective: every rank must make the same calls in the same order).       */
+int gpb_dist_unique_id(unsigned char* id128);
+int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q, gpb_dist_t** out);
+void gpb_dist_destroy(gpb_dist_t* dist);
+int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out);
+/* host arithmetic of the layout (no GPU needed): owner rank of block (I, J); staging order of the n_tiles blocks of
+ * panel k (tile t = block row k + t): process row o sends seg_count[o] tiles starting at slot seg_base[o], the first
+ * of which is tile seg_first[o], the following ones P apart.                                                    */
+int gpb_dist_owner(int I, int J, int P, int Q);
+int gpb_dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
 
 /* ---- utilities used by the host mirror and the tests --------------------------------------------------------- */
 /* C = alpha * op(A) op(B)^T + beta C on the FP64 tensor-core mainloop (a_kmajor: element (i,k) at A[k + i*lda]) */
