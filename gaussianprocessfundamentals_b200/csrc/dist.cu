@@ -169,11 +169,11 @@ struct GeoDistPanel {
   const GpbMat* mats;
   int k, P, p;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
+  __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "the in-place panel product needs full-width tiles");
     const GpbMat& d = mats[0];
     const int nrows = d.n + d.aug;
-    const int i0 = (k + 1) * GPB_NB + blockIdx.x * BM;
+    const int i0 = (k + 1) * GPB_NB + b.x * BM;
     if (i0 >= nrows) return false;
     if ((i0 / GPB_NB) % P != p) return false;
     double* Pn = d.A + (size_t)k * GPB_NB * d.ld + i0;
@@ -183,7 +183,7 @@ struct GeoDistPanel {
     J.mrem = min(BM, nrows - i0);
     J.nrem = GPB_NB;
     J.klo = 0; J.khi = GPB_NB;
-    J.alpha = 1.0; J.beta = 0.0;
+    J.alpha = 1.0; J.beta = 0.0; J.red = 0;
     return true;
   }
 };
@@ -194,14 +194,14 @@ struct GeoDistSyrk {
   const GpbMat* mats;
   int k, J_lo, J_hi, P, Q, p, q;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
+  __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "block columns are 128 wide");
     const GpbMat& d = mats[0];
     const int nrows = d.n + d.aug;
     const int Jf = J_lo + ((q - J_lo) % Q + Q) % Q;     // first block column >= J_lo owned by process column q
-    const int Jb = Jf + (int)blockIdx.y * Q;
+    const int Jb = Jf + (int)b.y * Q;
     if (Jb >= J_hi) return false;
-    const int row = Jb * GPB_NB + (int)blockIdx.x * BM;
+    const int row = Jb * GPB_NB + (int)b.x * BM;
     if (row >= nrows) return false;
     if ((row / GPB_NB) % P != p) return false;
     const size_t ld = d.ld;
@@ -213,7 +213,7 @@ struct GeoDistSyrk {
     J.mrem = min(BM, nrows - row);
     J.nrem = min(BN, nrows - Jb * GPB_NB);
     J.klo = 0; J.khi = GPB_NB;
-    J.alpha = -1.0; J.beta = 1.0;
+    J.alpha = -1.0; J.beta = 1.0; J.red = g_red_epilogue;
     return true;
   }
 };
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(const GpbMat* __res
 #define GPB_NK(x, where) do { if (!nccl_ok((x), where)) return cudaErrorUnknown; } while (0)
 
 template <class Cfg, class Geo>
-static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s) {
+static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
@@ -263,7 +263,7 @@ static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s) {
                                 Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_kernel<Cfg, false, false, Geo><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo);
+  gemm_kernel<Cfg, false, false, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
   return cudaGetLastError();
 }
@@ -360,7 +360,7 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
       const int nc = count_owned_cols(Jlo, Jhi, Q, q);
       if (nc == 0) return cudaSuccess;
       const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
-      return launch_geo<Cfg>(GeoDistSyrk{dm, k, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s);
+      return launch_geo<Cfg>(GeoDistSyrk{dm, k, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true);
     };
     if (k > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(k - 1) & 1], 0));
     GPB_CK(syrk(J1, J1 + 1, cs));

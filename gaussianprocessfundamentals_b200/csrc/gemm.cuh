@@ -14,11 +14,16 @@
 // lives at P[k + mn*ld] (column-major op(A)=A^T); both are supported for A and B so that NT / NN / TN products of
 // column-major matrices need no transposes in memory.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gpb {
 
 constexpr int G_BK = 16, G_STAGES = 3;
+#ifndef GPB_EPI
+#define GPB_EPI 4
+#endif
+constexpr int G_EPI = GPB_EPI;     // column groups (of 8) per epilogue batch
 constexpr int G_LDK = G_BK + 4;    // pitch (doubles) of a K-major tile    [rows][BK+4]
 
 template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int MIN_CTAS_>
@@ -34,6 +39,9 @@ struct GemmCfg {
 using CfgBig = GemmCfg<128, 128, 4, 2, 1>;
 using CfgHalf = GemmCfg<64, 128, 2, 2, 2>;
 
+// 1: accumulate-into epilogues (beta == 1) use RED; set per translation unit at init (GPB_RED=0 switches it off)
+static __constant__ int g_red_epilogue = 1;
+
 struct TileJob {
   const double* A;  // tile-row origin of op(A): MN-major -> &A[i0], K-major -> &A[i0*lda]
   const double* B;  // tile-col origin of op(B)
@@ -42,6 +50,7 @@ struct TileJob {
   int mrem, nrem;   // valid rows / cols of this tile
   int klo, khi;     // contraction range in operand coordinates
   double alpha, beta;
+  int red;          // beta == 1 and red != 0: C += alpha * acc through fire-and-forget RED.ADD.F64 (no read of C)
 };
 
 // one BK-deep slab of an operand tile with ROWS rows (m or n), by THREADS threads
@@ -77,125 +86,218 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, int ld, in
   }
 }
 
-template <class Cfg, bool AKM, bool BKM>
-__device__ __forceinline__ void gemm_tile(const TileJob& J) {
+// Per-thread constants of the fast (unpredicated) operand loads of full tiles: chunk q of a slab lives at
+// g + g_off + q * QROWS * ld in global memory (g = slab origin) and at s_off + q * S_Q in the stage buffer.
+template <bool KM, int ROWS, int THREADS>
+struct FastLoad {
+  static constexpr int PAIRS = ROWS / 2;
+  static constexpr int QROWS = KM ? THREADS / 8 : THREADS / PAIRS;   // operand rows (KM) / k rows (MN-major) per pass
+  static constexpr int NQ = KM ? ROWS / QROWS : G_BK / QROWS;
+  static constexpr int S_Q = KM ? QROWS * G_LDK : QROWS * (ROWS + 4);
+  static __device__ __forceinline__ void setup(int tid, int& r0, int& c0, int& s_off) {
+    if (!KM) { c0 = (tid % PAIRS) * 2; r0 = tid / PAIRS; s_off = r0 * (ROWS + 4) + c0; }   // r0: k row, c0: mn
+    else { c0 = (tid & 7) * 2; r0 = tid >> 3; s_off = r0 * G_LDK + c0; }                    // r0: mn row, c0: k
+  }
+};
+
+__device__ __forceinline__ void cp_async16_full(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// Tile loop of a CTA.  A CTA walks the virtual grid `vg` (the grid a one-tile-per-CTA launch would use) with stride
+// gridDim.x and keeps ONE cp.async pipeline running across tile boundaries: with fewer CTAs than tiles (persistent
+// launch) the first operand slabs of tile i+1 are in flight while tile i finishes, so a tile costs its k-steps plus its
+// epilogue and no pipeline fill; with gridDim.x = number of tiles it degenerates to one tile per CTA under the hardware
+// scheduler.  Full tiles (the overwhelming majority) take a fast path whose per-slab load issue is one address add
+// and one LDGSTS per 16-byte chunk and whose epilogue has no bounds checks; edge tiles keep the zero-filling loads.
+// Geometry functors map a virtual block index to a TileJob: `bool Geo::tile<BM, BN>(TileJob&, const dim3& b)`.
+template <class Cfg, bool AKM, bool BKM, class Geo>
+__device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
   extern __shared__ __align__(16) double gsm[];
   constexpr int BM = Cfg::BM, BN = Cfg::BN, T = Cfg::THREADS, FM = Cfg::FM, FN = Cfg::FN;
   constexpr int STAGE = Cfg::A_TILE + Cfg::B_TILE;
+  using FA = FastLoad<AKM, BM, T>;
+  using FB = FastLoad<BKM, BN, T>;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
   const int lr = lane >> 2, lk = lane & 3;
+  const unsigned total = vg.x * vg.y * vg.z;     // < 2^31 for every launch of the path
+  const unsigned stride = gridDim.x;
+  const bool flat = (vg.y == 1 && vg.z == 1);
+  int a_r0, a_c0, a_soff, b_r0, b_c0, b_soff;
+  FA::setup(tid, a_r0, a_c0, a_soff);
+  FB::setup(tid, b_r0, b_c0, b_soff);
 
-  double acc[FM][FN][2];
-#pragma unroll
-  for (int f = 0; f < FM; ++f)
-#pragma unroll
-    for (int g = 0; g < FN; ++g) { acc[f][g][0] = 0.0; acc[f][g][1] = 0.0; }
-
-  const int nk = (J.khi > J.klo) ? (J.khi - J.klo + G_BK - 1) / G_BK : 0;
-
-  if (J.beta != 0.0) {
-    // the accumulate-into tile is needed only by the epilogue: pull it into L2 now (BN columns x BM/16 lines)
-    constexpr int SEGS = BM / 16;
-#pragma unroll
-    for (int q = 0; q < (BN * SEGS + T - 1) / T; ++q) {
-      const int idx = tid + T * q;
-      const int col = idx / SEGS, seg = (idx % SEGS) * 16;
-      if (col < J.nrem && seg < J.mrem) {
-        const double* pp = J.C + (size_t)col * J.ldc + seg;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-      }
+  // next valid tile at or after idx
+  auto fetch = [&](unsigned& idx, TileJob& J) -> bool {
+    while (idx < total) {
+      dim3 b(idx, 0, 0);
+      if (!flat) { const unsigned xy = idx / vg.x; b.x = idx - xy * vg.x; b.z = xy / vg.y; b.y = xy - b.z * vg.y; }
+      if (geo.template tile<BM, BN>(J, b)) return true;
+      idx += stride;
     }
-  }
+    return false;
+  };
+  auto nk_of = [](const TileJob& J) { return (J.khi > J.klo) ? (J.khi - J.klo + G_BK - 1) / G_BK : 0; };
 
+  // ---- load cursor: runs up to G_STAGES-1 slabs ahead of the compute cursor, across tiles -------------------------
+  TileJob Jl;
+  unsigned lidx = blockIdx.x;
+  int l_kt = 0, l_nk = 0;
+  bool l_ok = false, l_fast = false;
+  const double* l_pa = nullptr;   // this thread's first chunk of the next slab (fast path)
+  const double* l_pb = nullptr;
+  auto next_load_tile = [&]() {
+    for (;;) {
+      l_ok = fetch(lidx, Jl);
+      if (!l_ok) return;
+      l_nk = nk_of(Jl);
+      if (l_nk > 0) break;
+      lidx += stride;
+    }
+    l_kt = 0;
+    l_fast = (Jl.mrem == BM) && (Jl.nrem == BN) && ((Jl.khi - Jl.klo) % G_BK == 0);
+    l_pa = AKM ? Jl.A + Jl.klo + a_c0 + (size_t)a_r0 * Jl.lda : Jl.A + a_c0 + (size_t)(Jl.klo + a_r0) * Jl.lda;
+    l_pb = BKM ? Jl.B + Jl.klo + b_c0 + (size_t)b_r0 * Jl.ldb : Jl.B + b_c0 + (size_t)(Jl.klo + b_r0) * Jl.ldb;
+  };
+  next_load_tile();
+  auto issue = [&](int stage) {
+    if (l_ok) {
+      double* Ns = gsm + stage * STAGE;
+      if (l_fast) {
 #pragma unroll
-  for (int s = 0; s < G_STAGES - 1; ++s) {
-    if (s < nk) {
-      double* As = gsm + s * STAGE;
-      load_tile<AKM, BM, T>(As, J.A, J.lda, J.mrem, J.klo + s * G_BK, J.khi, tid);
-      load_tile<BKM, BN, T>(As + Cfg::A_TILE, J.B, J.ldb, J.nrem, J.klo + s * G_BK, J.khi, tid);
+        for (int q = 0; q < FA::NQ; ++q)
+          cp_async16_full(Ns + a_soff + q * FA::S_Q, l_pa + (size_t)(q * FA::QROWS) * Jl.lda);
+#pragma unroll
+        for (int q = 0; q < FB::NQ; ++q)
+          cp_async16_full(Ns + Cfg::A_TILE + b_soff + q * FB::S_Q, l_pb + (size_t)(q * FB::QROWS) * Jl.ldb);
+        l_pa += AKM ? (size_t)G_BK : (size_t)G_BK * Jl.lda;
+        l_pb += BKM ? (size_t)G_BK : (size_t)G_BK * Jl.ldb;
+      } else {
+        load_tile<AKM, BM, T>(Ns, Jl.A, Jl.lda, Jl.mrem, Jl.klo + l_kt * G_BK, Jl.khi, tid);
+        load_tile<BKM, BN, T>(Ns + Cfg::A_TILE, Jl.B, Jl.ldb, Jl.nrem, Jl.klo + l_kt * G_BK, Jl.khi, tid);
+      }
+      if (++l_kt == l_nk) { lidx += stride; next_load_tile(); }
     }
     cp_async_commit();
-  }
+  };
+#pragma unroll
+  for (int s = 0; s < G_STAGES - 1; ++s) issue(s);
 
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<G_STAGES - 2>();
-    __syncthreads();
-    {
-      const int nt = kt + G_STAGES - 1;
-      if (nt < nk) {
-        double* Ns = gsm + (nt % G_STAGES) * STAGE;
-        load_tile<AKM, BM, T>(Ns, J.A, J.lda, J.mrem, J.klo + nt * G_BK, J.khi, tid);
-        load_tile<BKM, BN, T>(Ns + Cfg::A_TILE, J.B, J.ldb, J.nrem, J.klo + nt * G_BK, J.khi, tid);
-      }
-      cp_async_commit();
-    }
-    const double* As = gsm + (kt % G_STAGES) * STAGE;
-    const double* Bs = As + Cfg::A_TILE;
+  // ---- compute cursor -----------------------------------------------------------------------------------------------
+  TileJob J;
+  unsigned cidx = blockIdx.x;
+  int step = 0;   // slabs consumed so far (ring position)
+  while (fetch(cidx, J)) {
+    double acc[FM][FN][2];
 #pragma unroll
-    for (int kk = 0; kk < G_BK / 4; ++kk) {
-      const int kidx = kk * 4 + lk;
-      double a[FM], b[FN];
+    for (int f = 0; f < FM; ++f)
 #pragma unroll
-      for (int f = 0; f < FM; ++f) {
-        const int row = wm * Cfg::WM + f * 8 + lr;
-        a[f] = AKM ? As[row * G_LDK + kidx] : As[kidx * (BM + 4) + row];
-      }
-#pragma unroll
-      for (int g = 0; g < FN; ++g) {
-        const int col = wn * Cfg::WN + g * 8 + lr;
-        b[g] = BKM ? Bs[col * G_LDK + kidx] : Bs[kidx * (BN + 4) + col];
-      }
-#pragma unroll
-      for (int f = 0; f < FM; ++f)
-#pragma unroll
-        for (int g = 0; g < FN; ++g) dmma884(acc[f][g][0], acc[f][g][1], a[f], b[g]);
-    }
-  }
-  cp_async_wait<0>();
+      for (int g = 0; g < FN; ++g) { acc[f][g][0] = 0.0; acc[f][g][1] = 0.0; }
+    const int nk = nk_of(J);
 
-  // epilogue: each quad-row of 8 lanes covers 8 consecutive rows (64 B) of one column.  The C tile is read in
-  // batches (all loads of a batch issued before the first store) so that the read-modify-write costs FN/2 memory
-  // round trips per tile, not FM*FN*2.
-  const double alpha = J.alpha, beta = J.beta;
+    if (J.beta != 0.0 && !J.red) {
+      // the accumulate-into tile is needed only by the epilogue: pull it into L2 now (BN columns x BM/16 lines)
+      constexpr int SEGS = BM / 16;
 #pragma unroll
-  for (int gp = 0; gp < FN / 2; ++gp) {
-    double cv[2][2][FM];
-    if (beta != 0.0) {
+      for (int q = 0; q < (BN * SEGS + T - 1) / T; ++q) {
+        const int idx = tid + T * q;
+        const int col = idx / SEGS, seg = (idx % SEGS) * 16;
+        if (col < J.nrem && seg < J.mrem) {
+          const double* pp = J.C + (size_t)col * J.ldc + seg;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+        }
+      }
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+      cp_async_wait<G_STAGES - 2>();
+      __syncthreads();
+      issue((step + G_STAGES - 1) % G_STAGES);
+      const double* As = gsm + (step % G_STAGES) * STAGE;
+      const double* Bs = As + Cfg::A_TILE;
+      ++step;
 #pragma unroll
-      for (int gg = 0; gg < 2; ++gg)
+      for (int kk = 0; kk < G_BK / 4; ++kk) {
+        const int kidx = kk * 4 + lk;
+        double a[FM], b[FN];
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          const int row = wm * Cfg::WM + f * 8 + lr;
+          a[f] = AKM ? As[row * G_LDK + kidx] : As[kidx * (BM + 4) + row];
+        }
+#pragma unroll
+        for (int g = 0; g < FN; ++g) {
+          const int col = wn * Cfg::WN + g * 8 + lr;
+          b[g] = BKM ? Bs[col * G_LDK + kidx] : Bs[kidx * (BN + 4) + col];
+        }
+#pragma unroll
+        for (int f = 0; f < FM; ++f)
+#pragma unroll
+          for (int g = 0; g < FN; ++g) dmma884(acc[f][g][0], acc[f][g][1], a[f], b[g]);
+      }
+    }
+
+    // ---- epilogue: each quad-row of 8 lanes covers 8 consecutive rows (64 B) of one column -----------------------
+    const double alpha = J.alpha, beta = J.beta;
+    const bool full = (J.mrem == BM) && (J.nrem == BN);
+    double* c0 = J.C + (wm * Cfg::WM + lr) + (size_t)(wn * Cfg::WN + 2 * lk) * J.ldc;   // this thread's first element
+    const int rrem = J.mrem - (wm * Cfg::WM + lr), crem = J.nrem - (wn * Cfg::WN + 2 * lk);
+    if (J.red) {
+      // accumulate-into tile (beta == 1): every element of C is touched by exactly one thread of one CTA per launch,
+      // so the reduction is deterministic, and RED needs no round trip of C through the SM
+#pragma unroll
+      for (int g = 0; g < FN; ++g)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int col = wn * Cfg::WN + (2 * gp + gg) * 8 + 2 * lk + e;
-          const double* cp = J.C + (size_t)col * J.ldc;
+          double* cp = c0 + (size_t)(g * 8 + e) * J.ldc;
+          if (full || g * 8 + e < crem) {
 #pragma unroll
-          for (int f = 0; f < FM; ++f) {
-            const int row = wm * Cfg::WM + f * 8 + lr;
-            cv[gg][e][f] = (col < J.nrem && row < J.mrem) ? cp[row] : 0.0;
+            for (int f = 0; f < FM; ++f)
+              if (full || f * 8 < rrem) red_add_f64(cp + f * 8, alpha * acc[f][g][e]);
           }
         }
-    }
+    } else {
+      // read-modify-write in batches of G_EPI column groups (all loads of a batch issued before the first store)
 #pragma unroll
-    for (int gg = 0; gg < 2; ++gg)
+      for (int gp = 0; gp < FN / G_EPI; ++gp) {
+        double cv[G_EPI][2][FM];
+        if (beta != 0.0) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int g = 2 * gp + gg;
-        const int col = wn * Cfg::WN + g * 8 + 2 * lk + e;
-        if (col < J.nrem) {
-          double* cp = J.C + (size_t)col * J.ldc;
+          for (int gg = 0; gg < G_EPI; ++gg)
 #pragma unroll
-          for (int f = 0; f < FM; ++f) {
-            const int row = wm * Cfg::WM + f * 8 + lr;
-            if (row < J.mrem) {
-              double v = alpha * acc[f][g][e];
-              if (beta != 0.0) v += beta * cv[gg][e][f];
-              cp[row] = v;
+            for (int e = 0; e < 2; ++e) {
+              const int cc = (G_EPI * gp + gg) * 8 + e;
+              const double* cp = c0 + (size_t)cc * J.ldc;
+#pragma unroll
+              for (int f = 0; f < FM; ++f) cv[gg][e][f] = (full || (cc < crem && f * 8 < rrem)) ? cp[f * 8] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int gg = 0; gg < G_EPI; ++gg)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int g = G_EPI * gp + gg;
+            const int cc = g * 8 + e;
+            double* cp = c0 + (size_t)cc * J.ldc;
+            if (full || cc < crem) {
+#pragma unroll
+              for (int f = 0; f < FM; ++f) {
+                if (full || f * 8 < rrem) {
+                  double v = alpha * acc[f][g][e];
+                  if (beta != 0.0) v += beta * cv[gg][e][f];
+                  cp[f * 8] = v;
+                }
+              }
             }
           }
-        }
       }
+    }
+    cidx += stride;
   }
+  cp_async_wait<0>();
 }
 
 // Enumeration of the tiles of a lower-triangular region cut into (BM-row x BN-column) tiles, R = BN / BM:
@@ -207,25 +309,49 @@ __host__ __device__ inline long long tri_count(int Tm, int R, int c_lo, int c_hi
   const long long w = c_hi - c_lo, Tp = Tm - (long long)R * c_lo;
   return w * Tp - (long long)R * w * (w - 1) / 2;
 }
-__device__ __forceinline__ bool tri_map(long long idx, int Tm, int R, int c_lo, int c_hi, int& ti, int& tj) {
-  if (idx >= tri_count(Tm, R, c_lo, c_hi)) return false;
-  const long long Tp = Tm - (long long)R * c_lo;
-  const double b = (double)Tp + 0.5 * R;
-  long long c = (long long)floor((b - sqrt(b * b - 2.0 * R * (double)idx)) / (double)R);
-  if (c < 0) c = 0;
-  while (c > 0 && c * Tp - (long long)R * c * (c - 1) / 2 > idx) --c;
-  while ((c + 1) * Tp - (long long)R * (c + 1) * c / 2 <= idx) ++c;
-  const long long off = idx - (c * Tp - (long long)R * c * (c - 1) / 2);
-  tj = (int)c + c_lo;
-  ti = R * tj + (int)off;
+// 32-bit / single-precision fast path (every launch of the path: Tm <= 16384, so all counts fit in 31 bits): the
+// persistent kernel evaluates this twice per tile, so it must stay a few dozen instructions.
+__device__ __forceinline__ bool tri_map(unsigned idx, int Tm, int R, int c_lo, int c_hi, int& ti, int& tj) {
+  const int Tn = (Tm + R - 1) / R;
+  if (c_hi > Tn) c_hi = Tn;
+  if (c_hi <= c_lo) return false;
+  const int w = c_hi - c_lo, Tp = Tm - R * c_lo;
+  const int cnt = w * Tp - R * (w * (w - 1) / 2);
+  if (idx >= (unsigned)cnt) return false;
+  const float bq = (float)Tp + 0.5f * (float)R;
+  int c = (int)floorf((bq - sqrtf(fmaxf(bq * bq - 2.0f * (float)R * (float)idx, 0.0f))) / (float)R);
+  c = max(0, min(c, w - 1));
+  // prefix(c) = c * Tp - R * c (c - 1) / 2 tiles precede column c
+  while (c > 0 && c * Tp - R * (c * (c - 1) / 2) > (int)idx) --c;
+  while ((c + 1) * Tp - R * ((c + 1) * c / 2) <= (int)idx) ++c;
+  const int off = (int)idx - (c * Tp - R * (c * (c - 1) / 2));
+  tj = c + c_lo;
+  ti = R * tj + off;
   return true;
 }
 
 template <class Cfg, bool AKM, bool BKM, class Geo>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel(const Geo geo) {
-  TileJob J;
-  if (!geo.template tile<Cfg::BM, Cfg::BN>(J)) return;
-  gemm_tile<Cfg, AKM, BKM>(J);
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel(const Geo geo, const dim3 vgrid) {
+  gemm_stream<Cfg, AKM, BKM, Geo>(geo, vgrid);
+}
+
+// CTAs of a persistent launch: all tiles when they fit in one resident wave, else one resident wave
+inline unsigned persistent_ctas(dim3 vgrid, int min_ctas_per_sm, bool want_persistent = true) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("GPB_PERSIST");
+    persist = (e && e[0] == '0') ? 0 : 1;
+  }
+  const long long total = (long long)vgrid.x * vgrid.y * vgrid.z;
+  const long long wave = (long long)sms * min_ctas_per_sm;
+  return (unsigned)((total < wave || !persist || !want_persistent) ? total : wave);
 }
 
 }  // namespace gpb

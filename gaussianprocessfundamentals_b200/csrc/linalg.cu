@@ -24,14 +24,14 @@ struct GeoSyrk {
   const GpbMat* mats;
   int k, c_lo, c_hi;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
-    const GpbMat& d = mats[blockIdx.z];
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    const GpbMat& d = mats[b.z];
     const int nrows = d.n + d.aug;
     const int r0 = (k + 1) * GPB_NB;
     if (r0 >= nrows || (k + 1) * GPB_NB > d.n) return false;
     const int Tm = (nrows - r0 + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(blockIdx.x, Tm, BN / BM, c_lo, c_hi, ti, tj)) return false;
+    if (!tri_map(b.x, Tm, BN / BM, c_lo, c_hi, ti, tj)) return false;
     const size_t ld = d.ld;
     const double* P = d.A + (size_t)k * GPB_NB * ld;
     J.A = P + r0 + ti * BM;
@@ -41,7 +41,7 @@ struct GeoSyrk {
     J.mrem = min(BM, nrows - r0 - ti * BM);
     J.nrem = min(BN, nrows - r0 - tj * BN);
     J.klo = 0; J.khi = GPB_NB;
-    J.alpha = -1.0; J.beta = 1.0;
+    J.alpha = -1.0; J.beta = 1.0; J.red = g_red_epilogue;
     return true;
   }
 };
@@ -52,13 +52,13 @@ struct GeoPanel {
   const GpbMat* mats;
   int k;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
+  __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "the in-place panel product needs full-width tiles");
-    const GpbMat& d = mats[blockIdx.z];
+    const GpbMat& d = mats[b.z];
     const int nrows = d.n + d.aug;
     const int r0 = (k + 1) * GPB_NB;
     if (r0 > d.n) return false;  // block k is not a full pivot block
-    const int i0 = r0 + blockIdx.x * BM;
+    const int i0 = r0 + b.x * BM;
     if (i0 >= nrows) return false;
     const size_t ld = d.ld;
     double* P = d.A + (size_t)k * GPB_NB * ld + i0;
@@ -68,7 +68,7 @@ struct GeoPanel {
     J.mrem = min(BM, nrows - i0);
     J.nrem = GPB_NB;
     J.klo = 0; J.khi = GPB_NB;
-    J.alpha = 1.0; J.beta = 0.0;
+    J.alpha = 1.0; J.beta = 0.0; J.red = 0;
     return true;
   }
 };
@@ -80,13 +80,13 @@ struct GeoTrtriT {
   const GpbMat* mats;
   int s;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
-    const GpbMat& d = mats[blockIdx.z];
-    const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    const GpbMat& d = mats[b.z];
+    const int r0 = 2 * s * b.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
     const int tsn = s / BN;
-    const int ti = blockIdx.x / tsn, tj = blockIdx.x % tsn;
+    const int ti = b.x / tsn, tj = b.x % tsn;
     if (ti * BM >= M) return false;
     const size_t ld = d.ld;
     J.A = d.A + (rA + ti * BM) + (size_t)r0 * ld;
@@ -96,7 +96,7 @@ struct GeoTrtriT {
     J.mrem = min(BM, M - ti * BM);
     J.nrem = BN;
     J.klo = tj * BN; J.khi = s;
-    J.alpha = 1.0; J.beta = 0.0;
+    J.alpha = 1.0; J.beta = 0.0; J.red = 0;
     return true;
   }
 };
@@ -105,13 +105,13 @@ struct GeoTrtriW {
   const GpbMat* mats;
   int s;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
-    const GpbMat& d = mats[blockIdx.z];
-    const int r0 = 2 * s * blockIdx.y, rA = r0 + s;
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    const GpbMat& d = mats[b.z];
+    const int r0 = 2 * s * b.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
     const int tsn = s / BN;
-    const int ti = blockIdx.x / tsn, tj = blockIdx.x % tsn;
+    const int ti = b.x / tsn, tj = b.x % tsn;
     if (ti * BM >= M) return false;
     const size_t ld = d.ld;
     J.A = d.A + (rA + ti * BM) + (size_t)rA * ld;
@@ -121,7 +121,7 @@ struct GeoTrtriW {
     J.mrem = min(BM, M - ti * BM);
     J.nrem = BN;
     J.klo = 0; J.khi = min(M, (ti + 1) * BM);
-    J.alpha = -1.0; J.beta = 0.0;
+    J.alpha = -1.0; J.beta = 0.0; J.red = 0;
     return true;
   }
 };
@@ -130,11 +130,11 @@ struct GeoTrtriW {
 struct GeoLauum {
   const GpbMat* mats;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
-    const GpbMat& d = mats[blockIdx.z];
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    const GpbMat& d = mats[b.z];
     const int Tm = (d.n + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(blockIdx.x, Tm, BN / BM, 0, Tm, ti, tj)) return false;
+    if (!tri_map(b.x, Tm, BN / BM, 0, Tm, ti, tj)) return false;
     const size_t ld = d.ld;
     J.A = d.A + (size_t)(ti * BM) * ld;
     J.B = d.A + (size_t)(tj * BN) * ld;
@@ -143,7 +143,7 @@ struct GeoLauum {
     J.mrem = min(BM, d.n - ti * BM);
     J.nrem = min(BN, d.n - tj * BN);
     J.klo = ti * BM; J.khi = d.n;
-    J.alpha = 1.0; J.beta = 0.0;
+    J.alpha = 1.0; J.beta = 0.0; J.red = 0;
     return true;
   }
 };
@@ -153,14 +153,14 @@ struct GeoPlain {
   int lda, ldb, ldc, M, N, K, akm, bkm;
   double alpha, beta;
   template <int BM, int BN>
-  __device__ bool tile(TileJob& J) const {
-    const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    const int i0 = b.x * BM, j0 = b.y * BN;
     J.A = akm ? A + (size_t)i0 * lda : A + i0;
     J.B = bkm ? B + (size_t)j0 * ldb : B + j0;
     J.C = C + i0 + (size_t)j0 * ldc;
     J.lda = lda; J.ldb = ldb; J.ldc = ldc;
     J.mrem = min(BM, M - i0); J.nrem = min(BN, N - j0);
-    J.klo = 0; J.khi = K; J.alpha = alpha; J.beta = beta;
+    J.klo = 0; J.khi = K; J.alpha = alpha; J.beta = beta; J.red = (beta == 1.0) ? g_red_epilogue : 0;
     return true;
   }
 };
@@ -483,10 +483,12 @@ static bool cfg_half() {
   return g_cfg_half == 1;
 }
 
+// persistent = one resident wave of CTAs walking the tiles (equal-cost tiles: the trailing update); otherwise one CTA
+// per tile under the hardware scheduler (tiles of very different k-length: triangular inverse, W^T W)
 template <class Cfg, bool AKM, bool BKM, class Geo>
-static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s) {
+static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
-  gemm_kernel<Cfg, AKM, BKM, Geo><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo);
+  gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
   return cudaGetLastError();
 }
@@ -511,6 +513,11 @@ static cudaError_t set_smem_all() {
 }
 
 cudaError_t linalg_init() {
+  {
+    const char* e = getenv("GPB_RED");
+    const int v = (e && e[0] == '0') ? 0 : 1;
+    GPB_CK(cudaMemcpyToSymbol(g_red_epilogue, &v, sizeof(int)));
+  }
   GPB_CK(set_smem_all<CfgBig>());
   GPB_CK(set_smem_all<CfgHalf>());
   GPB_CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
@@ -540,7 +547,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     const int Tn = (rows + GPB_NB - 1) / GPB_NB;
     GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms)));
     if (!lookahead) {
-      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, Tn}, dim3((unsigned)tri_count(Tm, R, 0, Tn), 1, B), ms)));
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, Tn}, dim3((unsigned)tri_count(Tm, R, 0, Tn), 1, B), ms, true)));
       continue;
     }
     if (k > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(k - 1) & 1], 0));
@@ -549,7 +556,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[k & 1], 0));
     GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 1, 2}, dim3((unsigned)tri_count(Tm, R, 1, 2), 1, B), ex.side)));
     GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ex.side));
-    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 2, Tn}, dim3((unsigned)tri_count(Tm, R, 2, Tn), 1, B), ex.side)));
+    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 2, Tn}, dim3((unsigned)tri_count(Tm, R, 2, Tn), 1, B), ex.side, true)));
   }
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
