@@ -41,6 +41,7 @@ using CfgHalf = GemmCfg<64, 128, 2, 2, 2>;
 
 // 1: accumulate-into epilogues (beta == 1) use RED; set per translation unit at init (GPB_RED=0 switches it off)
 static __constant__ int g_red_epilogue = 1;
+static __constant__ int g_desync_cycles = 0;   // experiment: delay of the second resident wave's CTAs at kernel start
 
 struct TileJob {
   const double* A;  // tile-row origin of op(A): MN-major -> &A[i0], K-major -> &A[i0*lda]
@@ -83,6 +84,65 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, int ld, in
       const double* src = valid ? g + (k0 + k) + (size_t)mn * ld : g;
       cp_async16(s + mn * G_LDK + k, src, valid * 8);
     }
+  }
+}
+
+// Epilogue of one thread: acc[f][g][e] is element (f*8, g*8 + e) relative to the thread's first element c0.
+// FULL tiles carry no bounds checks.  Accumulate-into tiles (beta == 1, J.red): every element of C is touched by exactly
+// one thread of one CTA per launch, so RED.ADD.F64 is deterministic and C never travels through the SM; otherwise a
+// read-modify-write in batches of G_EPI column groups (all loads of a batch issued before the first store).
+template <class Cfg, bool FULL>
+__device__ __forceinline__ void gemm_epilogue(double (&acc)[Cfg::FM][Cfg::FN][2], const TileJob& J, double* c0, int rrem,
+                                              int crem) {
+  constexpr int FM = Cfg::FM, FN = Cfg::FN;
+  const double alpha = J.alpha, beta = J.beta;
+  const size_t ldc = J.ldc;
+  if (J.red) {
+#pragma unroll
+    for (int g = 0; g < FN; ++g)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double* cp = c0 + (size_t)(g * 8 + e) * ldc;
+        if (FULL || g * 8 + e < crem) {
+#pragma unroll
+          for (int f = 0; f < FM; ++f)
+            if (FULL || f * 8 < rrem) red_add_f64(cp + f * 8, alpha * acc[f][g][e]);
+        }
+      }
+    return;
+  }
+#pragma unroll
+  for (int gp = 0; gp < FN / G_EPI; ++gp) {
+    double cv[G_EPI][2][FM];
+    if (beta != 0.0) {
+#pragma unroll
+      for (int gg = 0; gg < G_EPI; ++gg)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cc = (G_EPI * gp + gg) * 8 + e;
+          const double* cp = c0 + (size_t)cc * ldc;
+#pragma unroll
+          for (int f = 0; f < FM; ++f) cv[gg][e][f] = (FULL || (cc < crem && f * 8 < rrem)) ? cp[f * 8] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int gg = 0; gg < G_EPI; ++gg)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int g = G_EPI * gp + gg;
+        const int cc = g * 8 + e;
+        double* cp = c0 + (size_t)cc * ldc;
+        if (FULL || cc < crem) {
+#pragma unroll
+          for (int f = 0; f < FM; ++f) {
+            if (FULL || f * 8 < rrem) {
+              double v = alpha * acc[f][g][e];
+              if (beta != 0.0) v += beta * cv[gg][e][f];
+              cp[f * 8] = v;
+            }
+          }
+        }
+      }
   }
 }
 
@@ -163,6 +223,10 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
     l_pb = BKM ? Jl.B + Jl.klo + b_c0 + (size_t)b_r0 * Jl.ldb : Jl.B + b_c0 + (size_t)(Jl.klo + b_r0) * Jl.ldb;
   };
   next_load_tile();
+  if (g_desync_cycles > 0 && stride < total && blockIdx.x >= stride / 2) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < g_desync_cycles) {}
+  }
   auto issue = [&](int stage) {
     if (l_ok) {
       double* Ns = gsm + stage * STAGE;
@@ -241,60 +305,10 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
     }
 
     // ---- epilogue: each quad-row of 8 lanes covers 8 consecutive rows (64 B) of one column -----------------------
-    const double alpha = J.alpha, beta = J.beta;
-    const bool full = (J.mrem == BM) && (J.nrem == BN);
     double* c0 = J.C + (wm * Cfg::WM + lr) + (size_t)(wn * Cfg::WN + 2 * lk) * J.ldc;   // this thread's first element
     const int rrem = J.mrem - (wm * Cfg::WM + lr), crem = J.nrem - (wn * Cfg::WN + 2 * lk);
-    if (J.red) {
-      // accumulate-into tile (beta == 1): every element of C is touched by exactly one thread of one CTA per launch,
-      // so the reduction is deterministic, and RED needs no round trip of C through the SM
-#pragma unroll
-      for (int g = 0; g < FN; ++g)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double* cp = c0 + (size_t)(g * 8 + e) * J.ldc;
-          if (full || g * 8 + e < crem) {
-#pragma unroll
-            for (int f = 0; f < FM; ++f)
-              if (full || f * 8 < rrem) red_add_f64(cp + f * 8, alpha * acc[f][g][e]);
-          }
-        }
-    } else {
-      // read-modify-write in batches of G_EPI column groups (all loads of a batch issued before the first store)
-#pragma unroll
-      for (int gp = 0; gp < FN / G_EPI; ++gp) {
-        double cv[G_EPI][2][FM];
-        if (beta != 0.0) {
-#pragma unroll
-          for (int gg = 0; gg < G_EPI; ++gg)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = (G_EPI * gp + gg) * 8 + e;
-              const double* cp = c0 + (size_t)cc * J.ldc;
-#pragma unroll
-              for (int f = 0; f < FM; ++f) cv[gg][e][f] = (full || (cc < crem && f * 8 < rrem)) ? cp[f * 8] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int gg = 0; gg < G_EPI; ++gg)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int g = G_EPI * gp + gg;
-            const int cc = g * 8 + e;
-            double* cp = c0 + (size_t)cc * J.ldc;
-            if (full || cc < crem) {
-#pragma unroll
-              for (int f = 0; f < FM; ++f) {
-                if (full || f * 8 < rrem) {
-                  double v = alpha * acc[f][g][e];
-                  if (beta != 0.0) v += beta * cv[gg][e][f];
-                  cp[f * 8] = v;
-                }
-              }
-            }
-          }
-      }
-    }
+    if ((J.mrem == BM) && (J.nrem == BN)) gemm_epilogue<Cfg, true>(acc, J, c0, rrem, crem);
+    else gemm_epilogue<Cfg, false>(acc, J, c0, rrem, crem);
     cidx += stride;
   }
   cp_async_wait<0>();

@@ -517,6 +517,9 @@ cudaError_t linalg_init() {
     const char* e = getenv("GPB_RED");
     const int v = (e && e[0] == '0') ? 0 : 1;
     GPB_CK(cudaMemcpyToSymbol(g_red_epilogue, &v, sizeof(int)));
+    const char* d = getenv("GPB_DESYNC");
+    const int dc = d ? atoi(d) : 0;
+    GPB_CK(cudaMemcpyToSymbol(g_desync_cycles, &dc, sizeof(int)));
   }
   GPB_CK(set_smem_all<CfgBig>());
   GPB_CK(set_smem_all<CfgHalf>());
