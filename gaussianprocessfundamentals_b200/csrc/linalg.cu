@@ -169,177 +169,202 @@ struct GeoPlain {
 // diagonal block: Cholesky of a 128 x 128 block in shared memory (+ rows of the carried y^T that fall inside the
 // block), log-det partial, then the block's triangular inverse for the panel product.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int D_LD = 132;    // pitch of the block in shared memory (conflict-free DMMA fragment reads)
-constexpr int D_TLD = 68;    // pitch of the 64 x 64 scratch of the in-block inverse
-constexpr int D_SMEM_BYTES = (GPB_NB * D_LD + 64 * D_TLD + 2 * GPB_NB + 16) * (int)sizeof(double);
+// The block and its inverse are computed TOGETHER by eliminating the augmented matrix [A; I] (256 x 128): the rows of
+// the identity are "carried rows" exactly like y^T in the big factorisation, and end up as I * L^-T = inv(L)^T.  The
+// elimination runs in 16 micro-panels of 8 columns:
+//   (1) panel: thread R (0..255) owns row R of the 8 panel columns.  The 8 x 8 diagonal micro-block is factorised
+//       redundantly by every warp (lane j < 8 holds its row j; pivots and multipliers travel by shuffle, so the pivot
+//       chain is shfl -> rsqrt -> mul -> shfl -> fma with no barrier and no shared memory), and every thread applies
+//       the same eliminations to its own row.  The finished panel goes to shared memory (DMMA operand layout), the
+//       L part also to global memory, the inv(L)^T part to a transposing buffer.
+//   (2) update: the trailing matrix lives in REGISTERS as DMMA accumulator fragments - 136 lower 8 x 8 tiles of A and
+//       136 upper tiles of X = inv(L)^T, 34 per warp, sorted by column so that the live ones form a suffix - and
+//       receives the rank-8 update  T(ti, tj) -= P(ti) P(tj)^T  as two DMMA.8x8x4 per tile.  The tiles of the next panel
+//       column are then published to shared memory in row-per-thread order.
+// Rows of the carried right-hand side that fall inside the block are ordinary non-pivot rows; a non-pivot column (the
+// element (n, n) behind y) is eliminated but never used as a pivot.
+constexpr int D_P = 264;                 // pitch of a panel buffer [8][D_P]: 256 rows per panel column
+constexpr int D_WLD = GPB_NB + 1;        // pitch of the transposing buffer of inv(L)
+constexpr int D_SLOTS = 34;              // register tiles per warp: 272 tiles / 8 warps
+constexpr int D_SMEM_BYTES = (2 * 8 * D_P + GPB_NB * D_WLD + GPB_NB) * (int)sizeof(double);
 
-// Cholesky of the block with the matrix held in registers: thread (lane, warp) owns rows lane+32a (a<4) and columns
-// warp+8b (b<16).  Column j is finished by its owner warp, published through shared memory (double buffered, one
-// barrier per column) and applied as a rank-1 update by everyone; JB = j / 8 is a compile-time constant so that all
-// register indices are static and the update loop shrinks as the factorisation proceeds.
-template <int JB>
-struct PotrfCols {
-  static __device__ __forceinline__ void run(double (&R)[4][16], double* col_s, int warp, int lane, int bf, int row0,
-                                             int* s_info) {
-    if (8 * JB >= bf) return;
-#pragma unroll 1
-    for (int jr = 0; jr < 8; ++jr) {
-      const int j = 8 * JB + jr;
-      if (j >= bf) break;
-      double* cs = col_s + (j & 1) * GPB_NB;
-      if (warp == jr) {
-        const double d = __shfl_sync(0xffffffffu, R[JB >> 2][JB], j & 31);
-        if (!(d > 0.0) && lane == 0 && *s_info == 0) *s_info = row0 + j + 1;
-        // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_jj = d * rsqrt(d): a third of the latency of
-        // sqrt followed by a division on the one chain of the factorisation that cannot be parallelised
-        const double inv = rsqrt(d);
-        const double ljj = d * inv;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int i = lane + 32 * a;
-          double v = R[a][JB] * inv;
-          if (i == j) v = ljj;
-          R[a][JB] = v;
-          cs[i] = v;
-        }
-      }
-      __syncthreads();
-      double lrow[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) lrow[a] = cs[lane + 32 * a];
-#pragma unroll
-      for (int b = JB; b < 16; ++b) {
-        if (b > JB || warp > jr) {
-          const double lc = cs[warp + 8 * b];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) R[a][b] = fma(-lrow[a], lc, R[a][b]);
-        }
-      }
-    }
-    PotrfCols<JB + 1>::run(R, col_s, warp, lane, bf, row0, s_info);
-  }
-};
-template <>
-struct PotrfCols<16> {
-  static __device__ __forceinline__ void run(double (&)[4][16], double*, int, int, int, int, int*) {}
-};
+// tile L = 8 * slot + warp of the column-sorted list: column tj holds 16 - tj lower tiles of A, then tj + 1 upper tiles of X
+__device__ __forceinline__ void diag_tile_of(int slot, int warp, int& ti, int& tj, bool& is_a) {
+  // slot is a compile-time constant at every call site: 8 * slot / 17 and the warp at which the column index steps
+  // fold to immediates, so the map costs a compare and two adds
+  const int base = 8 * slot, tj0 = base / 17, thr = 17 * (tj0 + 1) - base;
+  const int L = base + warp;
+  tj = tj0 + ((warp >= thr) ? 1 : 0);
+  const int t = L - 17 * tj;
+  is_a = t < 16 - tj;
+  ti = is_a ? tj + t : t - (16 - tj);
+}
 
 __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__ mats, int k) {
   extern __shared__ __align__(16) double dsm[];
-  double* As = dsm;                       // [128][D_LD]   L, then inv(L), column-major
-  double* Ts = As + GPB_NB * D_LD;        // [64][D_TLD]   scratch of the inverse
-  double* col_s = Ts + 64 * D_TLD;        // [2][128]      published column
-  double* red = col_s + 2 * GPB_NB;       // [8]
+  double* Xs = dsm;                  // [8][D_P]  next panel column, row-per-thread order
+  double* Ps = Xs + 8 * D_P;         // [8][D_P]  finished panel (DMMA operand)
+  double* Ws = Ps + 8 * D_P;         // [128][D_WLD]  W[a][b] = inv(L)[a][b]
+  double* piv = Ws + GPB_NB * D_WLD; // [128] pivots L_jj (their logs are taken after the elimination)
   __shared__ int s_info;
   const GpbMat d = mats[blockIdx.x];
   const int nrows = d.n + d.aug;
   const int r0 = k * GPB_NB;
   if (r0 >= d.n) return;
-  const int bs = min(GPB_NB, nrows - r0);  // rows held by the block (pivot rows + carried rows)
+  const int bs = min(GPB_NB, nrows - r0);  // rows / columns held by the block (pivots + carried)
   const int bf = min(GPB_NB, d.n - r0);    // pivots
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
   const size_t ld = d.ld;
   double* Ag = d.A + r0 + (size_t)r0 * ld;
-
   if (tid == 0) s_info = 0;
-  double R[4][16];
+
+  // ---- the augmented matrix as accumulator tiles ------------------------------------------------------------------
+  double acc[D_SLOTS][2];
 #pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    const int c = warp + 8 * b;
+  for (int s = 0; s < D_SLOTS; ++s) {
+    int ti, tj; bool is_a;
+    diag_tile_of(s, warp, ti, tj, is_a);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = lane + 32 * a;
-      R[a][b] = (i < bs && c < bs && i >= c) ? Ag[i + (size_t)c * ld] : 0.0;
+    for (int e = 0; e < 2; ++e) {
+      const int row = ti * 8 + lr, col = tj * 8 + 2 * lk + e;
+      double v;
+      if (is_a) v = (row < bs && col < bs && row >= col) ? Ag[row + (size_t)col * ld] : 0.0;
+      else v = (row == col) ? 1.0 : 0.0;
+      acc[s][e] = v;
+    }
+  }
+  // publish panel column 0
+#pragma unroll
+  for (int s = 0; s < D_SLOTS; ++s) {
+    int ti, tj; bool is_a;
+    diag_tile_of(s, warp, ti, tj, is_a);
+    if (tj == 0) {
+      const int rb = (is_a ? 0 : GPB_NB) + ti * 8 + lr;
+      Xs[(2 * lk) * D_P + rb] = acc[s][0];
+      Xs[(2 * lk + 1) * D_P + rb] = acc[s][1];
     }
   }
   __syncthreads();
-  PotrfCols<0>::run(R, col_s, warp, lane, bf, r0, &s_info);
 
-  // write L (zeros above the diagonal by construction) to global and to shared memory; log-det partial
+  const int R = tid;                       // row of [A; I] owned in the panel phase
+  const bool a_row = R < GPB_NB;
+  const int xi = R - GPB_NB;               // row of X (column of inv(L)) for the lower half
   double lsum = 0.0;
+  const int nsteps = (bs + 7) / 8;
+  for (int m = 0; m < nsteps; ++m) {
+    // ---- (1) panel ------------------------------------------------------------------------------------------------
+    const int c0 = 8 * m;
+    const bool active = a_row ? (R >= c0) : (xi < c0 + 8);
+    double a[8], Dr[8];
 #pragma unroll
-  for (int b = 0; b < 16; ++b) {
-    const int c = warp + 8 * b;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int i = lane + 32 * a;
-      const double v = R[a][b];
-      if (i < bs && c < bs) Ag[i + (size_t)c * ld] = v;
-      if (i == c && i < bf) lsum += log(v);
-      As[i + c * D_LD] = (i < bf && c < bf) ? v : ((i == c) ? 1.0 : 0.0);
+    for (int c = 0; c < 8; ++c) {
+      a[c] = active ? Xs[c * D_P + R] : 0.0;
+      Dr[c] = (lane < 8) ? Xs[c * D_P + c0 + lane] : 0.0;
     }
+    const int npiv = min(8, max(0, bf - c0));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double dv = __shfl_sync(0xffffffffu, Dr[c], c);
+      double inv = 1.0, lcc = dv;
+      if (c < npiv) {
+        if (!(dv > 0.0) && tid == 0 && s_info == 0) s_info = r0 + c0 + c + 1;
+        // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_cc = d * rsqrt(d): a third of the latency of
+        // sqrt followed by a division on the one chain of the factorisation that cannot be parallelised
+        inv = rsqrt(dv);
+        lcc = dv * inv;
+        if (warp == 7 && lane == c) piv[c0 + c] = lcc;
+      }
+      const double li = Dr[c] * inv;       // lane i > c: L[i][c] of the micro-block
+      double xc = a[c] * inv;
+      if (a_row && R - c0 == c) xc = lcc;  // the diagonal element itself
+#pragma unroll
+      for (int c2 = c + 1; c2 < 8; ++c2) {
+        const double l = __shfl_sync(0xffffffffu, li, c2);   // L[c2][c]
+        Dr[c2] = fma(-li, l, Dr[c2]);
+        a[c2] = fma(-xc, l, a[c2]);
+      }
+      a[c] = xc;
+    }
+    // rows of the micro-block itself: zero above the diagonal (those entries of the symmetric block were never loaded)
+    if (a_row && R >= c0 && R < c0 + 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c > R - c0) a[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double v = active ? a[c] : 0.0;
+      Ps[c * D_P + R] = v;
+      if (a_row) {
+        if (R < bs && c0 + c < bs) Ag[R + (size_t)(c0 + c) * ld] = v;     // L (explicit zeros above the diagonal)
+      } else {
+        Ws[(c0 + c) * D_WLD + xi] = v;                                   // inv(L)[c0 + c][xi] = X[xi][c0 + c]
+      }
+    }
+    __syncthreads();
+    // ---- (2) rank-8 update of the live tiles, publication of the next panel column -------------------------------
+    if (m + 1 < nsteps) {
+      // slots in chunks of 4: one uniform branch per chunk, straight-line inside (operands of dead tiles are zeroed),
+      // so that the 16 fragment loads and the 4 independent DMMA chains of a chunk overlap
+#pragma unroll
+      for (int s0 = 0; s0 < D_SLOTS; s0 += 4) {
+        int ti[4], tj[4]; bool is_a[4], act[4];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < D_SLOTS) {
+            diag_tile_of(s0 + u, warp, ti[u], tj[u], is_a[u]);
+            act[u] = tj[u] > m && (is_a[u] || ti[u] <= m);
+            any = any || act[u];
+          }
+        }
+        if (any) {
+          double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (s0 + u < D_SLOTS) {
+              const int ra = (is_a[u] ? 0 : GPB_NB) + ti[u] * 8 + lr;
+              const int rb = tj[u] * 8 + lr;
+              a0[u] = Ps[lk * D_P + ra]; a1[u] = Ps[(4 + lk) * D_P + ra];
+              b0[u] = Ps[lk * D_P + rb]; b1[u] = Ps[(4 + lk) * D_P + rb];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (s0 + u < D_SLOTS) dmma884(acc[s0 + u][0], acc[s0 + u][1], act[u] ? -a0[u] : 0.0, b0[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (s0 + u < D_SLOTS) dmma884(acc[s0 + u][0], acc[s0 + u][1], act[u] ? -a1[u] : 0.0, b1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < D_SLOTS && tj[u] == m + 1) {
+            const int rb = (is_a[u] ? 0 : GPB_NB) + ti[u] * 8 + lr;
+            Xs[(2 * lk) * D_P + rb] = acc[s0 + u][0];
+            Xs[(2 * lk + 1) * D_P + rb] = acc[s0 + u][1];
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
-  lsum = warp_sum(lsum);
-  if (lane == 0) red[warp] = lsum;
+
+  // ---- log-det partial, info, inv(L) to global memory -----------------------------------------------------------------
+  if (warp < 4) {
+    lsum = (tid < bf) ? log(piv[tid]) : 0.0;
+    lsum = warp_sum(lsum);
+    if (lane == 0) Xs[warp] = lsum;      // Xs is free after the last step
+  }
   __syncthreads();
   if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    d.part[k] = s;
+    d.part[k] = (Xs[0] + Xs[1]) + (Xs[2] + Xs[3]);
     if (s_info != 0 && *d.info == 0) *d.info = s_info;
-  }
-
-  // ---- in-block inverse: 32 x 32 diagonal blocks by forward substitution in registers (one warp each) ----------
-  if (warp < 4) {
-    const double* Ld = As + (32 * warp) + (32 * warp) * D_LD;
-    double bv[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) bv[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      const double wk = bv[kk] / Ld[kk + kk * D_LD];
-      bv[kk] = wk;
-#pragma unroll
-      for (int i = kk + 1; i < 32; ++i) bv[i] = fma(-Ld[i + kk * D_LD], wk, bv[i]);
-    }
-    __syncwarp();
-    double* Wd_ = As + (32 * warp) + (32 * warp + lane) * D_LD;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) Wd_[i] = bv[i];
-  }
-  __syncthreads();
-  // ---- recursive doubling on 8 x 8 DMMA tiles: W21 = -W22 * (L21 * W11) for s = 32, 64 --------------------------
-  const int lr = lane >> 2, lk = lane & 3;
-#pragma unroll 1
-  for (int s = 32; s <= 64; s *= 2) {
-    const int ts = s / 8;            // tiles per side of a sub-problem
-    const int nsub = 64 / s;
-    const int ntile = nsub * ts * ts;
-    for (int t = warp; t < ntile; t += 8) {
-      const int p = t / (ts * ts), tt = t % (ts * ts);
-      const int ti = tt / ts, tj = tt % ts;
-      const int b0 = 2 * s * p, rA = b0 + s;
-      double c0 = 0.0, c1 = 0.0;
-      for (int k4 = 2 * tj; k4 < s / 4; ++k4) {
-        const double a = As[(rA + ti * 8 + lr) + (b0 + k4 * 4 + lk) * D_LD];
-        const double b = As[(b0 + k4 * 4 + lk) + (b0 + tj * 8 + lr) * D_LD];
-        dmma884(c0, c1, a, b);
-      }
-      double* tp = Ts + (ti * 8 + lr) + (p * 32 + tj * 8 + 2 * lk) * D_TLD;
-      tp[0] = c0;
-      tp[D_TLD] = c1;
-    }
-    __syncthreads();
-    for (int t = warp; t < ntile; t += 8) {
-      const int p = t / (ts * ts), tt = t % (ts * ts);
-      const int ti = tt / ts, tj = tt % ts;
-      const int b0 = 2 * s * p, rA = b0 + s;
-      double c0 = 0.0, c1 = 0.0;
-      for (int k4 = 0; k4 < 2 * ti + 2; ++k4) {
-        const double a = As[(rA + ti * 8 + lr) + (rA + k4 * 4 + lk) * D_LD];
-        const double b = Ts[(k4 * 4 + lk) + (p * 32 + tj * 8 + lr) * D_TLD];
-        dmma884(c0, c1, a, b);
-      }
-      double* wp = As + (rA + ti * 8 + lr) + (b0 + tj * 8 + 2 * lk) * D_LD;
-      wp[0] = -c0;
-      wp[D_LD] = -c1;
-    }
-    __syncthreads();
   }
   double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
   for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
     const int i = idx & (GPB_NB - 1), j = idx >> 7;
-    Wg[idx] = (i >= j && i < bf) ? As[i + j * D_LD] : 0.0;
+    Wg[idx] = (i >= j && i < bf) ? Ws[i * D_WLD + j] : 0.0;
   }
 }
 
