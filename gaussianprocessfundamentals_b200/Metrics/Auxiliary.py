@@ -5,6 +5,7 @@ from ..Statistics import GaussianProcess as gp
 from . import MatrixHandlingTypes as mht
 from .BayesianInformationCriterion import BIC, BlockwiseBIC
 from .LogLikelihood import BlockwiseLogLikelihood, LogLikelihood
+from .MeanSquaredError import BlockwiseMeanSquaredError, MeanSquaredError
 from .Metrics import Metric, MetricType
 
 
@@ -23,8 +24,12 @@ def get_metric_by_type(metric_type: MetricType, _gp, local_approx=mht.MatrixAppr
     if metric_type is MetricType.blockwise_BIC:
         assert segmented, "Blockwise BIC may only be determined for blockwise Gaussian Process."
         return BlockwiseBIC(_gp, local_approx, numerical_matrix_handling, subset_size)
-    if metric_type in (MetricType.MSE, MetricType.blockwise_MSE):
-        raise NotImplementedError("MSE metrics are downstream of the likelihood path (SURVEY 8(f) #4)")
+    if metric_type is MetricType.MSE:
+        return MeanSquaredError(_gp.data_input, _gp.covariance_matrix, _gp.aux, local_approx, numerical_matrix_handling,
+                                subset_size)
+    if metric_type is MetricType.blockwise_MSE:
+        assert segmented, "Blockwise MSE may only be determined for blockwise Gaussian Process."
+        return BlockwiseMeanSquaredError(_gp, local_approx, numerical_matrix_handling, subset_size)
     logging.error("Invalid MetricType: %s" % str(metric_type))
     return None
 

@@ -292,3 +292,39 @@ def test_distances_and_prediction(gpb):
     var = gp.aux.get_posterior_var(hp, torch.tensor(1e-2, dtype=torch.float64)).cpu().numpy()
     Kss = np.exp(-0.5 * (xt - xt.T) ** 2 / 0.15 ** 2)
     assert np.max(np.abs(var - (Kss - Ks.T @ np.linalg.solve(K, Ks)))) <= 1e-7
+
+
+# ---- the callers right after the likelihood path: prediction, MSE, BIC (tests/golden/make_golden_predict.py) -------
+def test_prediction_mse_bic_match_reference(gpb):
+    g = gpb
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_predict.npz"))
+    meta = json.loads(bytes(z["__meta__"]).decode("utf-8"))
+    A = (g.mht.MatrixApproximations.NONE, g.mht.NumericalMatrixHandlingType.CHOLESKY_BASED)
+    for name, m in meta.items():
+        kern = build(g, json.loads(m["spec"]))
+        flat, hp, pos = z[name + "/hp"], [], 0
+        for d in kern.get_hyper_parameter_dimensionalities():
+            size = 1 if len(d) == 0 else d[0]
+            hp.append(torch.tensor(flat[pos:pos + size]).reshape(d))
+            pos += size
+        noise = torch.tensor(float(z[name + "/noise"]), dtype=torch.float64)
+        din = g.di.DataInput(z[name + "/x"], z[name + "/y"], z[name + "/xt"], z[name + "/yt"])
+        din.set_mean_function(g.bmf.ZeroMeanFunction(1))
+        gp = g.gproc.GaussianProcess(kern, g.bmf.ZeroMeanFunction(1))
+        gp.set_data_input(din)
+        mse = g.met_aux.get_metric_by_type(g.met.MetricType.MSE, gp, *A)
+        bic = g.met_aux.get_metric_by_type(g.met.MetricType.BIC, gp, *A)
+        v_mse, v_bic = float(mse.get_metric(hp, noise, None)), float(bic.get_metric(hp, noise, None))
+        assert abs(v_mse - float(z[name + "/mse"][0])) <= 1e-9 * abs(float(z[name + "/mse"][0])), name
+        assert abs(v_bic - float(z[name + "/bic"][0])) <= LL_RTOL * abs(float(z[name + "/bic"][0])), name
+        gp.aux.reset(); gp.covariance_matrix.reset()
+        mu = gp.aux.get_posterior_mu(hp, noise).cpu().numpy().reshape(-1)
+        scale = np.max(np.abs(z[name + "/post_mu"]))
+        assert np.max(np.abs(mu - z[name + "/post_mu"])) <= 1e-9 * scale, name
+        Ks = gp.covariance_matrix.get_K_s(hp).cpu().numpy()
+        assert np.max(np.abs(Ks - z[name + "/K_s"])) <= 1e-13 * np.max(np.abs(z[name + "/K_s"])), name
+        var = gp.aux.get_posterior_var(hp, noise).cpu().numpy()
+        # the posterior covariance is a difference of O(1) terms: absolute tolerance relative to the prior scale
+        assert np.max(np.abs(var - z[name + "/post_var"])) <= 1e-9 * max(1.0, np.max(np.abs(Ks))), name
+        total, mean_mu, post = gp.predict(hp, None, noise)
+        assert np.max(np.abs(total.cpu().numpy().reshape(-1) - z[name + "/predict_total"])) <= 1e-9 * scale, name
