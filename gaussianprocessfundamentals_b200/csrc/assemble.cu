@@ -40,11 +40,12 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   }
   int32_t* s_code = reinterpret_cast<int32_t*>(asm_smem);
   double* s_hp = reinterpret_cast<double*>(asm_smem + ((a.n_ops * GPB_OP_WORDS * 4 + 15) / 16) * 16);
-  double* s_xi = s_hp + ((a.n_hp + 1) / 2) * 2 + 2;
+  double* s_ihp = s_hp + ((a.n_hp + 1) / 2) * 2 + 2;       // 1 / hp: the per-entry path has no divisions
+  double* s_xi = s_ihp + ((a.n_hp + 1) / 2) * 2 + 2;
   double* s_xj = s_xi + A_T * a.dim;
   const int tid = threadIdx.x;
   for (int i = tid; i < a.n_ops * GPB_OP_WORDS; i += 256) s_code[i] = a.code[i];
-  for (int i = tid; i < a.n_hp; i += 256) s_hp[i] = a.hp[i];
+  for (int i = tid; i < a.n_hp; i += 256) { const double h = a.hp[i]; s_hp[i] = h; s_ihp[i] = 1.0 / h; }
   const double* Xc = a.X2 ? a.X2 : a.X;
   const long long i0 = (long long)ti * A_T, j0 = (long long)tj * A_T;
   for (int i = tid; i < A_T * a.dim; i += 256) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   const int r = tid & 63, cg = tid >> 6;
   const long long gi = i0 + r;
   GpbPair p;
-  p.xi = s_xi + r * a.dim; p.dim = a.dim; p.hp = s_hp; p.cp_mode = a.cp_mode; p.gi = gi;
+  p.xi = s_xi + r * a.dim; p.dim = a.dim; p.hp = s_hp; p.ihp = s_ihp; p.cp_mode = a.cp_mode; p.gi = gi;
   if (gi < a.n && own_main) {
 #pragma unroll 1
     for (int q = 0; q < A_T / 4; ++q) {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) assemble_rect_kernel(const AsmArgs a) {
 
 static size_t asm_smem_bytes(int n_ops, int n_hp, int dim) {
   size_t b = ((size_t)(n_ops * GPB_OP_WORDS * 4 + 15) / 16) * 16;
-  b += (size_t)(((n_hp + 1) / 2) * 2 + 2) * 8;
+  b += (size_t)2 * (((n_hp + 1) / 2) * 2 + 2) * 8;
   b += (size_t)2 * A_T * dim * 8;
   return b;
 }
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   const int P = d.n_hp + 1;
   double* s_acc = reinterpret_cast<double*>(g_smem);            // [acc_stride][256]
   double* s_hp = s_acc + (size_t)acc_stride * 256;
-  double* s_xi = s_hp + ((d.n_hp + 1) / 2) * 2 + 2;
+  double* s_ihp = s_hp + ((d.n_hp + 1) / 2) * 2 + 2;
+  double* s_xi = s_ihp + ((d.n_hp + 1) / 2) * 2 + 2;
   double* s_xj = s_xi + A_T * d.dim;
   double* s_ai = s_xj + A_T * d.dim;
   double* s_aj = s_ai + A_T;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   int32_t* s_code = reinterpret_cast<int32_t*>(s_red + 8);
   const int tid = threadIdx.x;
   for (int i = tid; i < d.n_ops * GPB_OP_WORDS; i += 256) s_code[i] = d.code[i];
-  for (int i = tid; i < d.n_hp; i += 256) s_hp[i] = d.hp[i];
+  for (int i = tid; i < d.n_hp; i += 256) { const double h = d.hp[i]; s_hp[i] = h; s_ihp[i] = 1.0 / h; }
   for (int p = 0; p < P; ++p) s_acc[p * 256 + tid] = 0.0;
   const int i0 = ti * A_T, j0 = tj * A_T;
   for (int i = tid; i < A_T * d.dim; i += 256) {
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   const int gi = i0 + r;
   SmemAcc acc{s_acc + tid};
   GpbPair p;
-  p.xi = s_xi + r * d.dim; p.dim = d.dim; p.hp = s_hp; p.cp_mode = d.cp_mode; p.gi = gi;
+  p.xi = s_xi + r * d.dim; p.dim = d.dim; p.hp = s_hp; p.ihp = s_ihp; p.cp_mode = d.cp_mode; p.gi = gi;
   if (gi < d.n) {
     const double ai = s_ai[r];
 #pragma unroll 1
@@ -209,7 +211,7 @@ int grad_tiles(int n) {
 
 static size_t grad_smem_bytes(int n_ops_max, int n_hp_max, int dim) {
   size_t b = (size_t)(n_hp_max + 1) * 256 * 8;
-  b += (size_t)(((n_hp_max + 1) / 2) * 2 + 2) * 8;
+  b += (size_t)2 * (((n_hp_max + 1) / 2) * 2 + 2) * 8;
   b += (size_t)2 * A_T * dim * 8 + (size_t)2 * A_T * 8 + 64;
   b += (size_t)n_ops_max * GPB_OP_WORDS * 4 + 16;
   return b;

@@ -50,16 +50,19 @@ struct GpbPair {
   int dim;
   long long gi, gj;  // global indices (white noise only)
   const double* hp;  // flat hyper-parameter vector
+  const double* ihp; // 1 / hp[i], precomputed once per CTA (the per-entry path has no divisions)
   int cp_mode;
 };
 
 // ---- distances (Auxiliary/Distances.py; r2 summed directly) ---------------------------------
 GPB_HD double gpb_sqdist(const GpbPair& p) {
+  if (p.dim == 1) { const double t = p.xi[0] - p.xj[0]; return t * t; }
   double r2 = 0.0;
   for (int d = 0; d < p.dim; ++d) { double t = p.xi[d] - p.xj[d]; r2 += t * t; }
   return r2;
 }
 GPB_HD double gpb_l1dist(const GpbPair& p) {
+  if (p.dim == 1) return fabs(p.xi[0] - p.xj[0]);
   double s = 0.0;
   for (int d = 0; d < p.dim; ++d) s += fabs(p.xi[d] - p.xj[d]);
   return s;
@@ -109,27 +112,32 @@ GPB_HD double gpb_cp_weight(const GpbPair& p, int hp_off, int i, int k, double* 
 GPB_HD double gpb_leaf(int op, int a, int flags, const GpbPair& p, double* dk) {
   const bool scaled = (flags & 1) != 0;
   const double* h = p.hp + a;
+  const double* ih = p.ihp + a;
   double k0 = 0.0;
   int nq = 0;
   switch (op) {
     case GPB_OP_SE: {
-      double l = h[0];
-      double r2 = gpb_sqdist(p);
-      k0 = exp(-0.5 * (r2 / (l * l)));
-      if (dk) dk[0] = k0 * r2 / (l * l * l);
+      const double il = ih[0];                 // 1 / l
+      const double r2 = gpb_sqdist(p);
+      const double q = r2 * (il * il);         // r2 / l^2
+      k0 = exp(-0.5 * q);
+      if (dk) dk[0] = k0 * q * il;             // k r2 / l^3
       nq = 1;
     } break;
     case GPB_OP_PER: {
-      double l = h[0], per = h[1];
-      double D = gpb_l1dist(p);
-      double u = M_PI * (D / per);
-      double s = sin(u);
-      double sine = s * s;
-      k0 = exp((-2.0 * sine) / (l * l));
+      const double il = ih[0], ip = ih[1];     // 1 / l, 1 / p
+      const double D = gpb_l1dist(p);
+      // the one true division of the path: u is the argument of sin and can be O(100), so an extra rounding of D / p
+      // would be amplified into the entry (the reference computes pi * (D / p), BaseKernels.py:447)
+      const double u = M_PI * (D / h[1]);
+      double s, c;
+      if (dk) sincos(u, &s, &c); else { s = sin(u); c = 0.0; }
+      const double sine = s * s;
+      const double il2 = il * il;
+      k0 = exp((-2.0 * sine) * il2);
       if (dk) {
-        double c = cos(u);
-        dk[0] = k0 * (4.0 * sine) / (l * l * l);
-        dk[1] = k0 * (2.0 * M_PI * D * (2.0 * s * c)) / (l * l * per * per);
+        dk[0] = k0 * (4.0 * sine) * (il2 * il);
+        dk[1] = k0 * (2.0 * M_PI * D * (2.0 * s * c)) * (il2 * (ip * ip));
       }
       nq = 2;
     } break;
@@ -141,22 +149,22 @@ GPB_HD double gpb_leaf(int op, int a, int flags, const GpbPair& p, double* dk) {
       nq = p.dim;
     } break;
     case GPB_OP_MAT32: {
-      double l = fabs(h[0]);
-      double D = gpb_l1dist(p);
-      double f = (sqrt(3.0) * D) / l;
-      double e = exp(-f);
+      const double il = fabs(ih[0]);           // 1 / |l|
+      const double D = gpb_l1dist(p);
+      const double f = (sqrt(3.0) * D) * il;
+      const double e = exp(-f);
       k0 = (1.0 + f) * e;
-      if (dk) dk[0] = (f * f * e / l) * (h[0] < 0.0 ? -1.0 : 1.0);
+      if (dk) dk[0] = (f * f * e * il) * (h[0] < 0.0 ? -1.0 : 1.0);
       nq = 1;
     } break;
     case GPB_OP_MAT52: {
-      double l = fabs(h[0]);
-      double D = gpb_l1dist(p);
-      double f = (sqrt(5.0) * D) / l;
-      double third = (5.0 * (D * D)) / (3.0 * (l * l));
-      double e = exp(-f);
+      const double il = fabs(ih[0]);
+      const double D = gpb_l1dist(p);
+      const double f = (sqrt(5.0) * D) * il;
+      const double third = (5.0 * (D * D)) * ((il * il) * (1.0 / 3.0));
+      const double e = exp(-f);
       k0 = (1.0 + f + third) * e;
-      if (dk) dk[0] = (f * f * (1.0 + f) / 3.0 * e / l) * (h[0] < 0.0 ? -1.0 : 1.0);
+      if (dk) dk[0] = (f * f * (1.0 + f) * (1.0 / 3.0) * e * il) * (h[0] < 0.0 ? -1.0 : 1.0);
       nq = 1;
     } break;
     case GPB_OP_WN: {
@@ -167,11 +175,11 @@ GPB_HD double gpb_leaf(int op, int a, int flags, const GpbPair& p, double* dk) {
     case GPB_OP_L1: return gpb_l1dist(p);
     case GPB_OP_SE_ARD: {
       double r2 = 0.0;
-      for (int d = 0; d < p.dim; ++d) { double t = (p.xi[d] - p.xj[d]) / h[d]; r2 += t * t; }
+      for (int d = 0; d < p.dim; ++d) { const double t = (p.xi[d] - p.xj[d]) * ih[d]; r2 += t * t; }
       k0 = exp(-0.5 * r2);
       if (dk) for (int d = 0; d < p.dim; ++d) {
-        double t = p.xi[d] - p.xj[d];
-        dk[d] = k0 * (t * t) / (h[d] * h[d] * h[d]);
+        const double t = (p.xi[d] - p.xj[d]) * ih[d];
+        dk[d] = k0 * (t * t) * ih[d];
       }
       nq = p.dim;
     } break;

@@ -12,7 +12,15 @@ extern "C" {
 int h_matrix(const int32_t* code, int n_ops, int dim, int cp_mode, const double* X, int n, const double* X2, int m,
              const double* hp, double* K, const double* W, double* grad) {
   GpbPair p;
-  p.dim = dim; p.hp = hp; p.cp_mode = cp_mode;
+  double ihp[GPB_MAX_HP + 1];
+  int n_hp = 0;
+  for (int pc = 0; pc < n_ops; ++pc) {
+    const int32_t* w = code + pc * GPB_OP_WORDS;
+    int top = w[1] + (w[0] < GPB_OP_ADD2 ? gpb_leaf_nhp(w[0], w[2], dim) : (w[0] == GPB_OP_CPW ? w[3] - 1 : 0));
+    if (top > n_hp) n_hp = top;
+  }
+  for (int i = 0; i < n_hp; ++i) ihp[i] = 1.0 / hp[i];
+  p.dim = dim; p.hp = hp; p.ihp = ihp; p.cp_mode = cp_mode;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < m; ++j) {
       p.xi = X + (size_t)i * dim; p.xj = X2 + (size_t)j * dim; p.gi = i; p.gj = j;
