@@ -263,7 +263,7 @@ static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool pe
                                 Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_kernel<Cfg, false, false, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
+  gemm_kernel<Cfg, false, false, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent ? 1 : 1), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
   return cudaGetLastError();
 }

@@ -349,8 +349,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel(const
   gemm_stream<Cfg, AKM, BKM, Geo>(geo, vgrid);
 }
 
-// CTAs of a persistent launch: all tiles when they fit in one resident wave, else one resident wave
-inline unsigned persistent_ctas(dim3 vgrid, int min_ctas_per_sm, bool want_persistent = true) {
+// CTAs of a launch over `vgrid` tiles.  max_tiles_per_cta = 1: one CTA per tile.  Larger values let a CTA keep its
+// cp.async pipeline running across up to that many tiles (no pipeline fill per tile), but never fewer CTAs than one
+// resident wave.  The bound keeps CTA lifetimes short: the kernels of the factorisation's critical path (diagonal block,
+// panel, NCCL broadcast) run on a high-priority stream and can only start when a CTA of the bulk update retires -
+// fully persistent CTAs serialised them behind the whole update (x1.25 on the distributed factorisation).
+inline unsigned persistent_ctas(dim3 vgrid, int min_ctas_per_sm, int max_tiles_per_cta) {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -358,14 +362,18 @@ inline unsigned persistent_ctas(dim3 vgrid, int min_ctas_per_sm, bool want_persi
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  static int persist = -1;
-  if (persist < 0) {
-    const char* e = getenv("GPB_PERSIST");
-    persist = (e && e[0] == '0') ? 0 : 1;
+  static int env_max = -1;
+  if (env_max < 0) {
+    const char* e = getenv("GPB_TILES_PER_CTA");
+    env_max = e ? atoi(e) : 0;
   }
+  if (env_max > 0 && max_tiles_per_cta > 1) max_tiles_per_cta = env_max;
   const long long total = (long long)vgrid.x * vgrid.y * vgrid.z;
+  if (max_tiles_per_cta <= 1) return (unsigned)total;
   const long long wave = (long long)sms * min_ctas_per_sm;
-  return (unsigned)((total < wave || !persist || !want_persistent) ? total : wave);
+  const long long bounded = (total + max_tiles_per_cta - 1) / max_tiles_per_cta;
+  long long g = total < wave ? total : (bounded > wave ? bounded : wave);
+  return (unsigned)g;
 }
 
 }  // namespace gpb

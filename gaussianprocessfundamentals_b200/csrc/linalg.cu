@@ -508,12 +508,14 @@ static bool cfg_half() {
   return g_cfg_half == 1;
 }
 
-// persistent = one resident wave of CTAs walking the tiles (equal-cost tiles: the trailing update); otherwise one CTA
-// per tile under the hardware scheduler (tiles of very different k-length: triangular inverse, W^T W)
+// persistent = CTAs walk up to TILES_PER_CTA tiles each (equal-cost tiles: the trailing update); otherwise one CTA per
+// tile under the hardware scheduler (tiles of very different k-length: triangular inverse, W^T W)
 template <class Cfg, bool AKM, bool BKM, class Geo>
 static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
+  constexpr int TILES_PER_CTA = 2;   // measured best on B200 (1: 425 ms, 2: 415 ms, 4: 416 ms, 8: 423 ms potrf at n = 32768)
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
-  gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
+  gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent ? TILES_PER_CTA : 1), Cfg::THREADS,
+                                   Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
   return cudaGetLastError();
 }
