@@ -166,3 +166,35 @@ def test_no_cpu_fallback():
     x = np.linspace(0, 1, 8)[:, None]
     with pytest.raises(_lib.GpbError):
         kern.get_tf_tensor([torch.tensor(0.1, dtype=torch.float64)], x, x)
+
+
+def test_distributed_layout_host_arithmetic():
+    """gpb_dist_owner / gpb_dist_panel_segments (include/gpb.h): the block -> rank map and the staging order of a panel's
+    tiles, against a plain restatement.  No GPU, no NCCL involved."""
+    import ctypes
+    lib = _lib.load()
+    for P, Q in ((1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (4, 2), (1, 8), (8, 1), (3, 2)):
+        for I in range(0, 20):
+            for J in range(0, 20):
+                assert lib.gpb_dist_owner(I, J, P, Q) == (I % P) * Q + (J % Q)
+        seen = set()
+        for I in range(P * 3):
+            for J in range(Q * 3):
+                seen.add(lib.gpb_dist_owner(I, J, P, Q))
+        assert seen == set(range(P * Q))                       # every rank owns blocks
+        for k in (0, 1, 5, 17):
+            for nt in (0, 1, 2, 7, 33):
+                base, cnt, first = ((ctypes.c_int * 8)(), (ctypes.c_int * 8)(), (ctypes.c_int * 8)())
+                assert lib.gpb_dist_panel_segments(k, nt, P, base, cnt, first) == 0
+                slots = {}
+                for o in range(P):
+                    tiles = [t for t in range(nt) if (k + t) % P == o]     # tiles of process row o, ascending
+                    assert cnt[o] == len(tiles)
+                    if tiles:
+                        assert first[o] == tiles[0]
+                    for idx, t in enumerate(tiles):
+                        slots[t] = base[o] + idx
+                # the staging order is a permutation of the panel's tiles, contiguous per process row
+                assert sorted(slots.values()) == list(range(nt))
+    assert lib.gpb_dist_owner(-1, 0, 1, 1) == -1
+    assert lib.gpb_dist_panel_segments(0, 4, 9, base, cnt, first) != 0      # P > 8 is refused
