@@ -344,6 +344,39 @@ __device__ __forceinline__ bool tri_map(unsigned idx, int Tm, int R, int c_lo, i
   return true;
 }
 
+// The same lower-triangular tile set in SUPER-TILE order: tile columns are taken in groups of G; inside a group the
+// row tiles run from the group's first diagonal tile to the bottom and the column index runs fastest.  Concurrently
+// running CTAs then cover ~(wave / G) row tiles x G column tiles instead of a whole column sweep, which cuts the distinct
+// operand columns a wave touches (and so the re-reads of a matrix larger than L2) by ~2.5x for a 296-CTA wave.
+__device__ __forceinline__ bool tri_map_grouped(unsigned idx, int Tm, int R, int G, int& ti, int& tj) {
+  const int Tn = (Tm + R - 1) / R;
+  int rem = (int)idx;
+  for (int g0 = 0; g0 < Tn; g0 += G) {
+    const int gw = min(G, Tn - g0);                 // columns of this group
+    const int row0 = R * g0;                        // first row tile of the group
+    const int rows = Tm - row0;
+    const int stair_rows = min(rows, R * gw);       // rows in which not every column of the group is reachable yet
+    // row r (relative) reaches floor(r / R) + 1 columns (capped at gw)
+    int stair = R * gw * (gw + 1) / 2;              // closed form when the staircase is complete
+    if (stair_rows < R * gw) { stair = 0; for (int r = 0; r < stair_rows; ++r) stair += min(gw, r / R + 1); }
+    const int cnt = stair + (rows - stair_rows) * gw;
+    if (rem < cnt) {
+      if (rem < stair) {
+        int r = 0;
+        for (;;) { const int w = min(gw, r / R + 1); if (rem < w) break; rem -= w; ++r; }
+        ti = row0 + r; tj = g0 + rem;
+      } else {
+        rem -= stair;
+        const int q = rem / gw;
+        ti = row0 + stair_rows + q; tj = g0 + (rem - q * gw);
+      }
+      return true;
+    }
+    rem -= cnt;
+  }
+  return false;
+}
+
 template <class Cfg, bool AKM, bool BKM, class Geo>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel(const Geo geo, const dim3 vgrid) {
   gemm_stream<Cfg, AKM, BKM, Geo>(geo, vgrid);

@@ -134,7 +134,7 @@ struct GeoLauum {
     const GpbMat& d = mats[b.z];
     const int Tm = (d.n + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(b.x, Tm, BN / BM, 0, Tm, ti, tj)) return false;
+    if (!tri_map_grouped(b.x, Tm, BN / BM, 8, ti, tj)) return false;   // super-tile raster: W exceeds L2
     const size_t ld = d.ld;
     J.A = d.A + (size_t)(ti * BM) * ld;
     J.B = d.A + (size_t)(tj * BN) * ld;
