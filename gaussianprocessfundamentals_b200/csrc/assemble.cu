@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   int ti, tj;
   if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
   const int P = d.n_hp + 1;
+  if (d.col_world && (tj / (GPB_NB / A_T)) % d.col_world != d.col_rank) {
+    // distributed plan: another rank owns this block column; its partial sums are zero here
+    for (int pp = threadIdx.x; pp < P; pp += 256) d.gpart[(size_t)blockIdx.x * P + pp] = 0.0;
+    return;
+  }
   double* s_acc = reinterpret_cast<double*>(g_smem);            // [acc_stride][256]
   double* s_hp = s_acc + (size_t)acc_stride * 256;
   double* s_ihp = s_hp + ((d.n_hp + 1) / 2) * 2 + 2;

@@ -243,9 +243,8 @@ int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, 
 int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out) {
   if (!prog) return fail_arg(1, "program is null");
   if (!dist || !dist->ctx) return fail_arg(4, "dist is null");
-  if (want_grad) return fail_arg(3, "distributed plans evaluate the likelihood only (stages ASSEMBLE | POTRF | NLL)");
   const gpb_program_t* progs[1] = {prog};
-  return plan_create(1, progs, &n, 0, dist->ctx, out);
+  return plan_create(1, progs, &n, want_grad, dist->ctx, out);
 }
 
 size_t gpb_plan_workspace_bytes(const gpb_plan_t* plan) { return plan ? plan->ws_bytes : 0; }
@@ -279,7 +278,10 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     d.info = (int*)(w + m.off[GPB_BUF_INFO]);
     d.n = (int)m.n; d.ld = m.ld; d.dim = g->dim; d.n_ops = g->n_ops; d.n_hp = g->n_hp; d.aug = 1;
     d.cp_mode = g->cp_mode; d.n_gtiles = m.n_gtiles;
-    if (p->dist) { d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q; }
+    if (p->dist) {
+      d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q;
+      d.col_world = p->dist->world; d.col_rank = p->dist->rank;
+    }
   }
   p->h_desc0 = h[0];
   CU(cudaMemcpy(p->ws + p->off_desc, h.data(), (size_t)p->B * sizeof(GpbMat), cudaMemcpyHostToDevice), "gpb_plan_bind");
@@ -308,8 +310,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
   p->ex.main = s;
   if (p->dist) {
-    if (stages & ~(GPB_STAGE_ASSEMBLE | GPB_STAGE_POTRF | GPB_STAGE_NLL))
-      return fail_arg(2, "distributed plans support the stages ASSEMBLE | POTRF | NLL");
+    if (stages & GPB_STAGE_BACKSOLVE) return fail_arg(2, "distributed plans do not implement BACKSOLVE");
     if (stages & GPB_STAGE_ASSEMBLE) {
       CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
       CU(gpb::run_assemble_batched(dm, 1, p->n_max, s), "assemble");
@@ -323,6 +324,25 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       }
     }
     if (stages & GPB_STAGE_NLL) CU(gpb::run_finalize_dist(dm, std::log(M_PI * 2.0), s), "finalize_dist");
+    auto dist_rc = [&](cudaError_t e, const char* where) -> int {
+      if (e == cudaSuccess) return 0;
+      if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }
+      return fail_cuda(e, where);
+    };
+    if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
+      int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), s), "trtri_dist");
+      if (rc) return rc;
+      CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
+    }
+    if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) {
+      int rc = dist_rc(gpb::run_lauum_dist(dm, p->h_desc0, *p->dist, s), "lauum_dist");
+      if (rc) return rc;
+    }
+    if (stages & GPB_STAGE_GRAD) {
+      CU(gpb::run_grad(dm, 1, p->n_max, p->n_hp_max, p->n_ops_max, p->dim, s), "grad");
+      int rc = dist_rc(gpb::run_grad_allreduce(p->h_desc0.grad, p->mats[0].n_hp + 1, *p->dist, s), "grad allreduce");
+      if (rc) return rc;
+    }
     return 0;
   }
   if (stages & GPB_STAGE_ASSEMBLE) {

@@ -27,6 +27,8 @@ struct GpbMat {
   int n, ld, dim, n_ops, n_hp, aug, cp_mode, n_gtiles;
   // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, J mod own_Q); own_P == 0: all
   int own_P, own_Q, own_p, own_q;
+  // gradient stages of a distributed plan: block column J belongs to rank J mod col_world (col_world == 0: all)
+  int col_world, col_rank;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {

@@ -20,6 +20,7 @@
 // high-priority stream, the bulk of the trailing update on the low-priority one (look-ahead), exactly as on one GPU.
 #include <dlfcn.h>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -334,12 +335,16 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     }
     // ---- exchange: pack own tiles, broadcast every process row's segment, unpack the others' tiles ------------
     const int t0 = (P > 1 && full) ? 1 : 0;                // the diagonal tile already travelled when P > 1
+    const bool ship_wd = (t0 == 0);                        // inv(L_kk) is replicated too: the later stages need all of them
     if (nt - t0 > 0) {
       if (q == qk) {
         panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 0);
         ++g_launches;
       }
+      if (ship_wd && D.rank == diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(st_wd, Wk); ++g_launches; }
       GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
+      if (ship_wd)
+        GPB_NK(g_nccl.Broadcast(st_wd, st_wd, TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(inv diag)");
       for (int o = 0; o < P; ++o) {
         int first = seg_base[o], cnt = seg_count[o];
         if (t0 == 1 && o == pk) { first += 1; cnt -= 1; }  // skip the diagonal tile (slot 0 of its owner's segment)
@@ -350,6 +355,7 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
       GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
       panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 1);
       ++g_launches;
+      if (ship_wd && D.rank != diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd); ++g_launches; }
     }
     if (!full) continue;
     GPB_CK(cudaEventRecord(ex.ev_e[k & 1], cs));
@@ -373,6 +379,170 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient stages of a distributed plan.  After the factorisation every rank holds the complete L and all inverted
+// diagonal blocks, so W = inv(L) and inv(K) = W^T W split by BLOCK COLUMN with no exchange inside a stage: rank r owns
+// the block columns J = r, r + world, ...  (1D, independent of the P x Q grid of the factorisation).
+//   trtri : X = W[:, J] for the own block columns by blocked forward substitution, right-looking, out of place in Kinv:
+//             step I:  X[I, J] <- -Wd_I * X[I, J]  (J < I; X[I, I] = Wd_I),  X[r, J] += L[r, I] * X[I, J]  for r > I
+//           (the second is a rank-128 update over all remaining rows - the same GEMM shape as the Cholesky trailing
+//           update), then ONE exchange: every block column is broadcast from its owner's Kinv into everybody's A.
+//   lauum : inv(K)[:, J] = W^T W[:, J] for the own block columns into Kinv (inputs: the full W, no exchange).
+//   grad  : the trace-gradient kernel over the own block columns, then one ncclAllReduce of n_hp + 1 doubles.
+// ---------------------------------------------------------------------------------------------------------------
+struct GeoDistTriDiag {     // T_J = -Wd_I * X[I, J]      (out of place: X[I, J] is the B operand)
+  const GpbMat* mats;
+  double* scratch;          // [nJ][128 x 128]
+  int I, world, rank;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    static_assert(BN == GPB_NB, "block columns are 128 wide");
+    const GpbMat& d = mats[0];
+    const int Jb = rank + (int)b.y * world;
+    if (Jb >= I) return false;
+    const int rows = min(GPB_NB, d.n - I * GPB_NB);
+    const int i0 = (int)b.x * BM;
+    if (i0 >= rows) return false;
+    J.A = d.Wd + (size_t)I * GPB_NB * GPB_NB + i0;                     // Wd_I rows i0.., MN-major, ld 128
+    J.B = d.Kinv + (size_t)I * GPB_NB + (size_t)Jb * GPB_NB * d.ld;    // X[I, J]: element (col, k) at [k + col * ld]
+    J.C = scratch + (size_t)b.y * GPB_NB * GPB_NB + i0;
+    J.lda = GPB_NB; J.ldb = d.ld; J.ldc = GPB_NB;
+    J.mrem = min(BM, rows - i0); J.nrem = GPB_NB;
+    J.klo = 0; J.khi = min(rows, i0 + BM);                              // Wd_I is lower triangular
+    J.alpha = -1.0; J.beta = 0.0; J.red = 0;
+    return true;
+  }
+};
+
+struct GeoDistTriUpdate {   // X[r, J] += L[r, I] * X[I, J]  for r > I, J <= I own
+  const GpbMat* mats;
+  int I, world, rank;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    static_assert(BN == GPB_NB, "block columns are 128 wide");
+    const GpbMat& d = mats[0];
+    const int Jb = rank + (int)b.y * world;
+    if (Jb > I) return false;
+    const int row = (I + 1) * GPB_NB + (int)b.x * BM;
+    if (row >= d.n) return false;
+    const size_t ld = d.ld;
+    J.A = d.A + row + (size_t)I * GPB_NB * ld;                         // L[r, I], MN-major
+    J.B = d.Kinv + (size_t)I * GPB_NB + (size_t)Jb * GPB_NB * ld;      // X[I, J], K-major
+    J.C = d.Kinv + row + (size_t)Jb * GPB_NB * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(BM, d.n - row); J.nrem = GPB_NB;
+    J.klo = 0; J.khi = GPB_NB;
+    J.alpha = 1.0; J.beta = 1.0; J.red = g_red_epilogue;
+    return true;
+  }
+};
+
+struct GeoDistLauum {       // inv(K)[ti, J] = sum_{k >= ti} W[k, ti]^T W[k, J] for the own block columns J
+  const GpbMat* mats;
+  int world, rank;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    static_assert(BN == GPB_NB, "block columns are 128 wide");
+    const GpbMat& d = mats[0];
+    const int Jb = rank + (int)b.y * world;
+    const int col0 = Jb * GPB_NB;
+    if (col0 >= d.n) return false;
+    const int row = col0 + (int)b.x * BM;                               // lower tiles: rows from the diagonal block down
+    if (row >= d.n) return false;
+    const size_t ld = d.ld;
+    J.A = d.A + (size_t)row * ld;
+    J.B = d.A + (size_t)col0 * ld;
+    J.C = d.Kinv + row + (size_t)col0 * ld;
+    J.lda = J.ldb = J.ldc = d.ld;
+    J.mrem = min(BM, d.n - row); J.nrem = min(BN, d.n - col0);
+    J.klo = row; J.khi = d.n;
+    J.alpha = 1.0; J.beta = 0.0; J.red = 0;
+    return true;
+  }
+};
+
+// X[I, J] <- T_J for the own J < I, X[I, I] <- Wd_I when block column I is own
+__global__ void __launch_bounds__(256) tri_diag_store_kernel(const GpbMat* __restrict__ mats, const double* __restrict__ scratch,
+                                                             int I, int world, int rank) {
+  const GpbMat d = mats[0];
+  const int Jb = rank + (int)blockIdx.x * world;
+  if (Jb > I) return;
+  const int rows = min(GPB_NB, d.n - I * GPB_NB);
+  const double* src = (Jb == I) ? d.Wd + (size_t)I * GPB_NB * GPB_NB : scratch + (size_t)blockIdx.x * GPB_NB * GPB_NB;
+  const int cols = min(GPB_NB, d.n - Jb * GPB_NB);
+  double* dst = d.Kinv + (size_t)I * GPB_NB + (size_t)Jb * GPB_NB * d.ld;
+  for (int idx = threadIdx.x; idx < GPB_NB * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), c = idx >> 7;
+    if (i < rows && c < cols) dst[i + (size_t)c * d.ld] = src[idx];
+  }
+}
+
+template <class Cfg, bool AKM, bool BKM, class Geo>
+static cudaError_t launch_geo2(const Geo& geo, dim3 grid, cudaStream_t s) {
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPB_CK(cudaFuncSetAttribute(gemm_kernel<Cfg, AKM, BKM, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, 1), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(geo, grid);
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+static int own_cols_upto(int J_incl, int world, int rank) {   // own block columns J <= J_incl
+  return J_incl < rank ? 0 : (J_incl - rank) / world + 1;
+}
+
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s) {
+  using Cfg = CfgHalf;
+  const int n = h.n, world = D.world, rank = D.rank;
+  const int nblk = (n + GPB_NB - 1) / GPB_NB;
+  const size_t ld = h.ld;
+  // zero the own block columns of X (the accumulation starts from 0; rows above the diagonal block stay 0 = W's zeros)
+  for (int J = rank; J < nblk; J += world) {
+    const int cols = std::min(GPB_NB, n - J * GPB_NB);
+    GPB_CK(cudaMemsetAsync(h.Kinv + (size_t)J * GPB_NB * ld, 0, (size_t)cols * ld * sizeof(double), s));
+  }
+  for (int I = 0; I < nblk; ++I) {
+    const int nJ_lt = own_cols_upto(I - 1, world, rank);     // own J < I
+    const int nJ_le = own_cols_upto(I, world, rank);         // own J <= I
+    if (nJ_le == 0) continue;
+    if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), s)));
+    tri_diag_store_kernel<<<nJ_le, 256, 0, s>>>(dm, scratch, I, world, rank);
+    ++g_launches;
+    GPB_CK(cudaGetLastError());
+    const int rows = n - (I + 1) * GPB_NB;
+    if (rows > 0)
+      GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriUpdate{dm, I, world, rank}, dim3((rows + Cfg::BM - 1) / Cfg::BM, nJ_le, 1), s)));
+  }
+  // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
+  for (int J0 = 0; J0 < nblk; J0 += 64) {
+    GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
+    for (int J = J0; J < std::min(nblk, J0 + 64); ++J) {
+      const int cols = std::min(GPB_NB, n - J * GPB_NB);
+      GPB_NK(g_nccl.Broadcast(h.Kinv + (size_t)J * GPB_NB * ld, h.A + (size_t)J * GPB_NB * ld, (size_t)cols * ld, NCCL_F64,
+                              J % world, D.comm, s), "ncclBroadcast(W)");
+    }
+    GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+  }
+  return cudaSuccess;
+}
+
+cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, cudaStream_t s) {
+  using Cfg = CfgHalf;
+  const int nblk = (h.n + GPB_NB - 1) / GPB_NB;
+  const int nJ = own_cols_upto(nblk - 1, D.world, D.rank);
+  const int Tm = (h.n + Cfg::BM - 1) / Cfg::BM;
+  return launch_geo2<Cfg, true, true>(GeoDistLauum{dm, D.world, D.rank}, dim3(Tm, nJ, 1), s);
+}
+
+cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s) {
+  GPB_NK(g_nccl.AllReduce(grad, grad, (size_t)count, NCCL_F64, NCCL_SUM, D.comm, s), "ncclAllReduce(grad)");
   return cudaSuccess;
 }
 

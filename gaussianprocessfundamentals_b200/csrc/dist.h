@@ -20,6 +20,9 @@ void dist_destroy(DistCtx* d);
 void dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
 size_t dist_stage_bytes(int n);
 cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex);
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s);
+cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, cudaStream_t s);
+cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s);
 cudaError_t run_finalize_dist(const GpbMat* dm, double log2pi, cudaStream_t s);
 
 }  // namespace gpb

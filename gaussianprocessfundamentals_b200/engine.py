@@ -98,7 +98,8 @@ class Plan:
     def __init__(self, programs: Sequence[DeviceProgram], ns: Sequence[int], want_grad: bool = True,
                  device: Optional[torch.device] = None, grid: Optional["ProcessGrid"] = None):
         """grid: a ProcessGrid makes this the distributed plan of ONE GP (2D block-cyclic block ownership, NCCL panel
-        broadcasts; likelihood stages only).  Every rank of the grid must construct it and call eval collectively."""
+        broadcasts; inverse and gradient split by block column).  Every rank of the grid must construct it and call
+        eval collectively."""
         require_cuda()
         lib = _lib.load()
         self.lib = lib
@@ -113,9 +114,10 @@ class Plan:
         h = ctypes.c_void_p()
         self.grid = grid
         if grid is not None:
-            if self.B != 1 or want_grad:
-                raise _lib.GpbError("a distributed plan holds one GP and evaluates the likelihood only")
-            _lib.check(lib.gpb_plan_create_dist(self.programs[0].handle, self.ns[0], 0, grid.handle, ctypes.byref(h)),
+            if self.B != 1:
+                raise _lib.GpbError("a distributed plan holds one GP")
+            _lib.check(lib.gpb_plan_create_dist(self.programs[0].handle, self.ns[0], 1 if want_grad else 0, grid.handle,
+                                                ctypes.byref(h)),
                        "gpb_plan_create_dist")
         else:
             _lib.check(lib.gpb_plan_create(self.B, handles, n_arr, 1 if want_grad else 0, ctypes.byref(h)),

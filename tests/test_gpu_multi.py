@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 LL_RTOL = 1e-10     # north-star tolerance on the log-likelihood
+GRAD_RTOL = 1e-8    # ... and on the gradient
 
 
 def _ngpu():
@@ -83,16 +84,35 @@ def _dist_worker(rank, world, port, cases, out):
             nll_d2 = dp.results()[0]
             # host-buffer call
             nll_h, _, info_h = dp.eval_host([hp], [1e-2], [x], [y.reshape(-1)], stages=eng.STAGES_LML)
+            # gradient stages: W = inv(L) and inv(K) split by block column, one all-reduce of the gradient
+            refg = eng.Plan([prog], [n], want_grad=True)
+            refg.set_data(0, torch.tensor(x), torch.tensor(y)); refg.set_hp(0, hp, 1e-2)
+            refg.eval(eng.STAGES_LML_GRAD)
+            nll_rg, g_ref, _ = refg.results()
+            dpg = eng.Plan([prog], [n], want_grad=True, grid=grid)
+            dpg.set_data(0, torch.tensor(x), torch.tensor(y)); dpg.set_hp(0, hp, 1e-2)
+            dpg.eval(eng.STAGES_LML_GRAD)
+            torch.cuda.synchronize()
+            nll_g, g_d, info_g = dpg.results()
+            dW = float((dpg.lower_matrix(0) - refg.lower_matrix(0))[tril].abs().max())
+            Wmax = float(refg.lower_matrix(0)[tril].abs().max())
+            dalpha = float((dpg.buffer(0, eng.BUF_ALPHA) - refg.buffer(0, eng.BUF_ALPHA)).abs().max())
+            amax = float(refg.buffer(0, eng.BUF_ALPHA).abs().max())
+            dpg.eval(eng.STAGES_LML_GRAD)
+            torch.cuda.synchronize()
+            g_d2 = dpg.results()[1]
             res.append(dict(n=n, d=d, P=P, Q=Q, nll_ref=float(nll_ref[0]), nll=float(nll_d[0]), nll2=float(nll_d2[0]),
                             nll_host=float(nll_h[0]), info=int(info_d[0]), info_ref=int(info_ref[0]), dL=dL, dz=dz,
-                            Lmax=float(L_ref[tril].abs().max())))
-            del ref, dp
+                            Lmax=float(L_ref[tril].abs().max()), nll_grad_run=float(nll_g[0]), info_g=int(info_g[0]),
+                            grad=[float(v) for v in g_d[0]], grad_ref=[float(v) for v in g_ref[0]],
+                            grad2=[float(v) for v in g_d2[0]], dW=dW, Wmax=Wmax, dalpha=dalpha, amax=amax))
+            del ref, dp, refg, dpg
             torch.cuda.empty_cache()
         # non positive definite input: every rank must report the same pivot
         n = 700
         tree, hp, x, y = _problem(n, 1, 3)
         prog = eng.DeviceProgram.get(tree, 1, False, 1)
-        dp = eng.Plan([prog], [n], want_grad=False, grid=grids[cases[0][2:]])
+        dp = eng.Plan([prog], [n], want_grad=False, grid=grids[tuple(cases[0][2:])])
         dp.set_data(0, torch.tensor(x), torch.tensor(y)); dp.set_hp(0, hp, -5.0)
         dp.eval(eng.STAGES_LML)
         nll_bad, _, info_bad = dp.results()
@@ -141,6 +161,12 @@ def test_distributed_cholesky_matches_single_gpu():
             assert r["nll_host"] == r["nll"], tag
             assert r["dL"] <= 1e-12 * r["Lmax"], tag
             assert r["dz"] <= 1e-9, tag
+            assert r["info_g"] == 0 and abs(r["nll_grad_run"] - r["nll_ref"]) <= LL_RTOL * abs(r["nll_ref"]), tag
+            g, gr = np.asarray(r["grad"]), np.asarray(r["grad_ref"])
+            assert np.max(np.abs(g - gr)) <= GRAD_RTOL * np.max(np.abs(gr)), tag
+            assert r["grad2"] == r["grad"], tag
+            assert r["dW"] <= 1e-10 * r["Wmax"], tag
+            assert r["dalpha"] <= 1e-9 * r["amax"], tag
         assert res[-1]["bad_info"] > 0 and res[-1]["bad_nll_isnan"]
     # every rank reports the same numbers
     for r0, r1 in zip(got[0][1], got[-1][1]):
