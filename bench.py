@@ -40,7 +40,13 @@ WORKLOADS = {
                tree=("SE_ARD",), hp=None, d=8),
     "c5s": dict(name="C5 at n=32768: SE-ARD, d=8, LML (distributed Cholesky, NCCL panel broadcasts)", n=32768, B=1,
                 tree=("SE_ARD",), hp=None, d=8),
+    # the same with the gradient stages (distributed inverse + trace gradient), strong scaling
+    "c5g": dict(name="C5 + gradient: SE-ARD, n=65536, d=8, LML+grad (distributed Cholesky, inverse, trace gradient)",
+                n=65536, B=1, tree=("SE_ARD",), hp=None, d=8, grad=True),
+    "m32kd": dict(name="M32k distributed: SE-ARD, n=32768, d=8, LML+grad over N GPUs (strong scaling)", n=32768, B=1,
+                  tree=("SE_ARD",), hp=None, d=8, grad=True),
 }
+DIST_WORKLOADS = ("c5", "c5s", "c5g", "m32kd")
 
 
 # ---- synthetic data --------------------------------------------------------------------------------------
@@ -197,8 +203,8 @@ def make_c5(n, d, seed=4):
 
 
 def run_c5(args, rank, world, local_rank):
-    """LML (no gradient) of one n-point SE-ARD GP: N = 1 single-GPU plan, N > 1 distributed Cholesky.  Strong scaling:
-    the work is fixed, value = evaluations / s of the whole job."""
+    """LML (workloads with grad=True: LML + gradient) of one n-point SE-ARD GP: N = 1 single-GPU plan, N > 1 distributed
+    plan.  Strong scaling: the work is fixed, value = evaluations / s of the whole job."""
     import torch
     import torch.distributed as dist
     from gaussianprocessfundamentals_b200 import _lib, engine as eng
@@ -207,13 +213,15 @@ def run_c5(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOADS[args.workload]
     n, d = w["n"], w["d"]
+    want_grad = bool(w.get("grad", False))
+    STAGES = eng.STAGES_LML_GRAD if want_grad else eng.STAGES_LML
     x, y, ell = make_c5(n, d)
     prog = eng.DeviceProgram.get(w["tree"], d, False, 1)
     grid = None
     if world > 1:
         P, Q = (args.grid if args.grid else eng.ProcessGrid.default_shape(world))
         grid = eng.ProcessGrid(P, Q)
-    plan = eng.Plan([prog], [n], want_grad=False, grid=grid)
+    plan = eng.Plan([prog], [n], want_grad=want_grad, grid=grid)
     plan.set_data(0, torch.tensor(x), torch.tensor(y))
     plan.set_hp(0, ell, 1e-2)
 
@@ -227,18 +235,20 @@ def run_c5(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     l0 = eng.launch_count()
-    plan.eval(eng.STAGES_LML)
+    plan.eval(STAGES)
     torch.cuda.synchronize()
     launches = eng.launch_count() - l0
     stage_ms = {}
-    marks = [ev() for _ in range(4)]
+    names = ["assemble", "potrf", "nll"] + (["trtri", "lauum", "grad"] if want_grad else [])
+    bits = [eng.STAGE_ASSEMBLE, eng.STAGE_POTRF, eng.STAGE_NLL] + \
+        ([eng.STAGE_TRTRI, eng.STAGE_LAUUM, eng.STAGE_GRAD] if want_grad else [])
+    marks = [ev() for _ in range(len(bits) + 1)]
     barrier()
     marks[0].record()
-    plan.eval(eng.STAGE_ASSEMBLE); marks[1].record()
-    plan.eval(eng.STAGE_POTRF); marks[2].record()
-    plan.eval(eng.STAGE_NLL); marks[3].record()
+    for i, bit in enumerate(bits):
+        plan.eval(bit); marks[i + 1].record()
     barrier()
-    for i, name in enumerate(["assemble", "potrf", "nll"]):
+    for i, name in enumerate(names):
         stage_ms[name] = marks[i].elapsed_time(marks[i + 1])
     lib = _lib.load()
     best = 1e9
@@ -249,14 +259,14 @@ def run_c5(args, rank, world, local_rank):
         best = min(best, e0.elapsed_time(e1))
     dmma_peak = 148 * 4 * 8 * 20000 * 8 * 512 / (best * 1e-3) / 1e12
     for _ in range(args.warmup):
-        plan.eval(eng.STAGES_LML)
+        plan.eval(STAGES)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
-        plan.eval(eng.STAGES_LML)
+        plan.eval(STAGES)
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -264,26 +274,30 @@ def run_c5(args, rank, world, local_rank):
     nll, _, info = plan.results()
     # e2e: host buffers in, scalars out, every step
     hx, hy = torch.tensor(x).pin_memory().numpy(), torch.tensor(y.reshape(-1)).pin_memory().numpy()
-    plan.eval_host([ell], [1e-2], [hx], [hy], stages=eng.STAGES_LML)
+    plan.eval_host([ell], [1e-2], [hx], [hy], stages=STAGES)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
-        plan.eval_host([ell], [1e-2], [hx], [hy], stages=eng.STAGES_LML)
+        plan.eval_host([ell], [1e-2], [hx], [hy], stages=STAGES)
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, stage_ms["potrf"]], dtype=torch.float64, device="cuda")
+        keys = sorted(stage_ms)
+        t = torch.tensor([elapsed_ms, e2e_ms] + [stage_ms[k_] for k_ in keys], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, stage_ms["potrf"] = float(t[0]), float(t[1]), float(t[2])
+        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        for i, k_ in enumerate(keys):
+            stage_ms[k_] = float(t[2 + i])
     if rank == 0:
         value = args.steps / (elapsed_ms * 1e-3)
         flops = n ** 3 / 3.0
         tf = flops / (stage_ms["potrf"] * 1e-3) / 1e12
         line = {
-            "metric": "LML evals/sec (likelihood only; distributed Cholesky)", "value": value, "unit": "evals/s",
+            "metric": METRIC if want_grad else "LML evals/sec (likelihood only; distributed Cholesky)", "value": value,
+            "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "noise": 1e-2,
@@ -291,7 +305,8 @@ def run_c5(args, rank, world, local_rank):
                        "multi_gpu": "2D block-cyclic block ownership, NCCL panel broadcasts" if grid else "single GPU",
                        "l2": "working set (%.1f GiB) exceeds the 126 MB L2; no explicit flush" % (8.0 * n * n / 2 ** 30)},
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
-                    "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + ell.nbytes + 8), "d2h_bytes_per_step": 8 + 4,
+                    "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + ell.nbytes + 8),
+                    "d2h_bytes_per_step": 8 + 4 + (8 * (d + 1) if want_grad else 0),
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches * args.steps), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "Cholesky (gemm_kernel trailing updates + panels + diagonal blocks), "
@@ -351,7 +366,7 @@ def main():
         run_reference(args, rank, world)
         return
 
-    if args.workload in ("c5", "c5s"):
+    if args.workload in DIST_WORKLOADS:
         run_c5(args, rank, world, local_rank)
         return
 

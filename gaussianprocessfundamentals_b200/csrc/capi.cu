@@ -62,6 +62,12 @@ struct gpb_plan {
   bool own_streams;
   char* h_in;   // pinned mirror of the small input region
   char* h_out;  // pinned mirror of the small output region
+  // CUDA graph of the launch sequence of gpb_plan_eval_host (one per stage mask), replayed on a private stream
+  cudaStream_t gstream;
+  cudaEvent_t g_in, g_out;
+  int graph_stages[4];
+  cudaGraphExec_t graph_exec[4];
+  int n_graphs, graphs_off;
   gpb::DistCtx* dist;       // non-null: ONE GP factorised over a process grid (dist.cu)
   size_t off_stage[2];      // panel staging buffers of a distributed plan
   GpbMat h_desc0;           // host copy of the first descriptor (distributed plans)
@@ -230,6 +236,14 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
+  p->n_graphs = 0; p->graphs_off = 0; p->gstream = nullptr;
+  {
+    const char* ge = getenv("GPB_GRAPH");
+    if (ge && ge[0] == '0') p->graphs_off = 1;
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->g_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->g_out, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete p; return fail_cuda(e, "gpb_plan_create"); }
   p->own_streams = true;
   *out = p;
@@ -385,8 +399,41 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
   }
   memcpy(p->h_in + (p->off_noise_all - p->off_in), noise_host, (size_t)p->B * 8);
   CU(cudaMemcpyAsync(p->ws + p->off_in, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, s), "H2D hp");
-  int rc = gpb_plan_eval(p, stages, stream);
-  if (rc) return rc;
+  int rc = 0;
+  // The launch sequence (hundreds of kernels on three streams for a large matrix, dozens for a small one) is captured
+  // once per stage mask and replayed: the inputs live at fixed addresses inside the workspace.  Distributed plans launch
+  // directly (their NCCL calls are ordered with the other ranks by the host loop).
+  cudaGraphExec_t exec = nullptr;
+  if (!p->dist && !p->graphs_off) {
+    for (int i = 0; i < p->n_graphs; ++i)
+      if (p->graph_stages[i] == stages) exec = p->graph_exec[i];
+    if (!exec && p->n_graphs < 4) {
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(p->gstream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        rc = gpb_plan_eval(p, stages, (void*)p->gstream);
+        ce = cudaStreamEndCapture(p->gstream, &graph);
+        if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (rc != 0 || ce != cudaSuccess || !exec) {
+        (void)cudaGetLastError();
+        exec = nullptr; rc = 0; p->graphs_off = 1;           // capture is best effort: fall back to direct launches
+      } else {
+        p->graph_stages[p->n_graphs] = stages; p->graph_exec[p->n_graphs] = exec; ++p->n_graphs;
+      }
+    }
+  }
+  if (exec) {
+    CU(cudaEventRecord(p->g_in, s), "graph fork");
+    CU(cudaStreamWaitEvent(p->gstream, p->g_in, 0), "graph fork");
+    CU(cudaGraphLaunch(exec, p->gstream), "graph launch");
+    CU(cudaEventRecord(p->g_out, p->gstream), "graph join");
+    CU(cudaStreamWaitEvent(s, p->g_out, 0), "graph join");
+  } else {
+    rc = gpb_plan_eval(p, stages, stream);
+    if (rc) return rc;
+  }
   CU(cudaMemcpyAsync(p->h_out, p->ws + p->off_out, p->out_bytes, cudaMemcpyDeviceToHost, s), "D2H results");
   CU(cudaStreamSynchronize(s), "sync");
   if (nll_host) memcpy(nll_host, p->h_out + (p->off_nll_all - p->off_out), (size_t)p->B * 8);
@@ -404,6 +451,8 @@ void gpb_plan_destroy(gpb_plan_t* p) {
       cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_join[i]);
     }
     cudaEventDestroy(p->ex.ev_fork);
+    for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);
+    if (p->gstream) { cudaStreamDestroy(p->gstream); cudaEventDestroy(p->g_in); cudaEventDestroy(p->g_out); }
   }
   if (p->h_in) cudaFreeHost(p->h_in);
   if (p->h_out) cudaFreeHost(p->h_out);
