@@ -18,29 +18,31 @@ namespace gpb {
 // GEMM geometries (tile<BM, BN>() fills the job of the calling CTA; BN is always 128 = GPB_NB)
 // ---------------------------------------------------------------------------------------------------------------
 
-// trailing update of step k: A[r0:, r0:] -= P P^T with P = A[r0:, k*128 : k*128 + kw], lower tiles, tile columns
-// restricted to [c_lo, c_hi) so that the look-ahead driver can split the update across streams.
+// trailing update with the panel P = A[r0:, kp*128 : (kp+kb)*128] (kb = 1 or 2 finished 128-blocks):
+// A[r0:, r0:] -= P P^T for r0 = (kp+kb)*128, lower tiles, tile columns restricted to [c_lo, c_hi) so that the look-ahead
+// driver can split the update across streams.  kb = 2 halves the number of passes over the far trailing matrix and the
+// per-tile epilogue cost per flop (k = 256: 31 TFLOP/s against 28 at k = 128).
 struct GeoSyrk {
   const GpbMat* mats;
-  int k, c_lo, c_hi;
+  int kp, kb, c_lo, c_hi;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
     const int nrows = d.n + d.aug;
-    const int r0 = (k + 1) * GPB_NB;
-    if (r0 >= nrows || (k + 1) * GPB_NB > d.n) return false;
+    const int r0 = (kp + kb) * GPB_NB;
+    if (r0 >= nrows || r0 > d.n) return false;   // every block of the panel must be a full pivot block
     const int Tm = (nrows - r0 + BM - 1) / BM;
     int ti, tj;
     if (!tri_map(b.x, Tm, BN / BM, c_lo, c_hi, ti, tj)) return false;
     const size_t ld = d.ld;
-    const double* P = d.A + (size_t)k * GPB_NB * ld;
+    const double* P = d.A + (size_t)kp * GPB_NB * ld;
     J.A = P + r0 + ti * BM;
     J.B = P + r0 + tj * BN;
     J.C = d.A + (r0 + ti * BM) + (size_t)(r0 + tj * BN) * ld;
     J.lda = J.ldb = J.ldc = d.ld;
     J.mrem = min(BM, nrows - r0 - ti * BM);
     J.nrem = min(BN, nrows - r0 - tj * BN);
-    J.klo = 0; J.khi = GPB_NB;
+    J.klo = 0; J.khi = kb * GPB_NB;
     J.alpha = -1.0; J.beta = 1.0; J.red = g_red_epilogue;
     return true;
   }
@@ -554,39 +556,84 @@ cudaError_t linalg_init() {
   return cudaSuccess;
 }
 
+// outer panel width of the factorisation in 128-blocks.  Measured on B200 (potrf, ms, kb = 1 / 2): n = 4096 3.16 / 3.43,
+// 8192 10.08 / 9.91, 16384 56.9 / 52.9, 32768 411 / 380 - the wider panel pays once the far update dominates.
+// GPB_POTRF_KB=1|2 overrides.
+static int kb_max(int n_max) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GPB_POTRF_KB");
+    forced = e ? ((e[0] == '1') ? 1 : 2) : 0;
+  }
+  if (forced) return forced;
+  return n_max >= 6144 ? 2 : 1;
+}
+
+// Blocked right-looking Cholesky.  Diagonal blocks and panels are 128 wide; two consecutive panels are applied to the
+// far trailing matrix together (k = 256).  With look-ahead (one large matrix) the critical path - diagonal block, panel,
+// the strip update of the second block column, and the first far column - runs on a high-priority stream so that its
+// few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream, which does
+// the columns the next outer step needs first and then the bulk.
 template <class Cfg>
 static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
   constexpr int BM = Cfg::BM, R = Cfg::BN / Cfg::BM;
   const int nrows = n_max + aug;
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
-  // With look-ahead the critical path (diagonal block -> panel -> next panel column) runs on a high-priority stream so
-  // that its few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream.
   cudaStream_t ms = lookahead ? ex.crit : ex.main;
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
     GPB_CK(cudaStreamWaitEvent(ex.crit, ex.ev_fork, 0));
     GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_fork, 0));
   }
-  for (int k = 0; k < nblk; ++k) {
+  auto full_with_rows = [&](int k) {   // block k (of the largest matrix) is a full pivot block with rows below it
+    return k < nblk && (k + 1) * GPB_NB <= n_max && nrows - (k + 1) * GPB_NB > 0;
+  };
+  auto diag = [&](int k) -> cudaError_t {
     diag_kernel<<<B, 256, D_SMEM_BYTES, ms>>>(dm, k);
     ++g_launches;
-    GPB_CK(cudaGetLastError());
-    const int rows = nrows - (k + 1) * GPB_NB;   // rows below the diagonal block
-    if (rows <= 0 || (k + 1) * GPB_NB > n_max) continue;
+    return cudaGetLastError();
+  };
+  auto panel = [&](int k) -> cudaError_t {
+    const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
+    return launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms);
+  };
+  auto syrk = [&](int kp, int kb, int c_lo, int c_hi, cudaStream_t st, bool bulk) -> cudaError_t {
+    const int rows = nrows - (kp + kb) * GPB_NB;
+    if (rows <= 0) return cudaSuccess;
     const int Tm = (rows + BM - 1) / BM;
-    const int Tn = (rows + GPB_NB - 1) / GPB_NB;
-    GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms)));
-    if (!lookahead) {
-      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, Tn}, dim3((unsigned)tri_count(Tm, R, 0, Tn), 1, B), ms, true)));
-      continue;
+    return launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi},
+                                         dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk);
+  };
+  int step = 0;
+  for (int k = 0; k < nblk;) {
+    GPB_CK(diag(k));
+    if (!full_with_rows(k)) { ++k; continue; }
+    GPB_CK(panel(k));
+    int kb = 1;
+    bool waited = false;
+    if (kb_max(n_max) > 1 && full_with_rows(k + 1)) {
+      // block column k+1 received its far update from the previous outer step on the side stream
+      if (lookahead && step > 0) { GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(step - 1) & 1], 0)); waited = true; }
+      GPB_CK(syrk(k, 1, 0, 1, ms, false));          // block column k+1 <- panel k (inside the 256-wide outer panel)
+      GPB_CK(diag(k + 1));
+      GPB_CK(panel(k + 1));
+      kb = 2;
     }
-    if (k > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(k - 1) & 1], 0));
-    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 0, 1}, dim3((unsigned)tri_count(Tm, R, 0, 1), 1, B), ms)));
-    GPB_CK(cudaEventRecord(ex.ev_e[k & 1], ms));
-    GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[k & 1], 0));
-    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 1, 2}, dim3((unsigned)tri_count(Tm, R, 1, 2), 1, B), ex.side)));
-    GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ex.side));
-    GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, k, 2, Tn}, dim3((unsigned)tri_count(Tm, R, 2, Tn), 1, B), ex.side, true)));
+    const int rows = nrows - (k + kb) * GPB_NB;
+    const int Tn = (rows + GPB_NB - 1) / GPB_NB;
+    if (!lookahead) {
+      GPB_CK(syrk(k, kb, 0, Tn, ms, true));
+    } else {
+      if (step > 0 && !waited) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(step - 1) & 1], 0));
+      GPB_CK(syrk(k, kb, 0, 1, ms, false));                       // the next diagonal block's column
+      GPB_CK(cudaEventRecord(ex.ev_e[step & 1], ms));
+      GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[step & 1], 0));
+      GPB_CK(syrk(k, kb, 1, 1 + kb, ex.side, false));             // the columns the next outer step touches first
+      GPB_CK(cudaEventRecord(ex.ev_g[step & 1], ex.side));
+      GPB_CK(syrk(k, kb, 1 + kb, Tn, ex.side, true));
+    }
+    k += kb;
+    ++step;
   }
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
