@@ -6,6 +6,7 @@
 // Operands are staged with 16-byte cp.async (zero-filling out-of-range rows / k) into padded, bank-conflict-free
 // shared-memory tiles, 3 stages deep.  Two tile configurations share the code:
 //   CfgBig   128 x 128, 8 warps (4 x 2), warp tile 32 x 64, one CTA per SM
+//   CfgQuarter 32 x 128, 4 warps (1 x 4), warp tile 32 x 32, for launches smaller than one wave of CfgHalf tiles
 //   CfgHalf   64 x 128, 4 warps (2 x 2), warp tile 32 x 64, two CTAs per SM (the second CTA hides the first one's
 //             barrier / prologue / epilogue bubbles; twice as many CTAs for the single-wave launches of the
 //             factorisation's critical path)
@@ -38,10 +39,12 @@ struct GemmCfg {
 };
 using CfgBig = GemmCfg<128, 128, 4, 2, 1>;
 using CfgHalf = GemmCfg<64, 128, 2, 2, 2>;
+// 32 x 128, 4 warps (1 x 4), warp tile 32 x 32: for the single-wave launches of the factorisation's critical path (panel
+// solve, next-column update) - twice the CTAs of CfgHalf at half the tile latency when the launch has < 148 tiles anyway
+using CfgQuarter = GemmCfg<32, 128, 1, 4, 2>;
 
 // 1: accumulate-into epilogues (beta == 1) use RED; set per translation unit at init (GPB_RED=0 switches it off)
 static __constant__ int g_red_epilogue = 1;
-static __constant__ int g_desync_cycles = 0;   // experiment: delay of the second resident wave's CTAs at kernel start
 
 struct TileJob {
   const double* A;  // tile-row origin of op(A): MN-major -> &A[i0], K-major -> &A[i0*lda]
@@ -223,10 +226,6 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
     l_pb = BKM ? Jl.B + Jl.klo + b_c0 + (size_t)b_r0 * Jl.ldb : Jl.B + b_c0 + (size_t)(Jl.klo + b_r0) * Jl.ldb;
   };
   next_load_tile();
-  if (g_desync_cycles > 0 && stride < total && blockIdx.x >= stride / 2) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < g_desync_cycles) {}
-  }
   auto issue = [&](int stage) {
     if (l_ok) {
       double* Ns = gsm + stage * STAGE;

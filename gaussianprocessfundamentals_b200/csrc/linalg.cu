@@ -546,14 +546,19 @@ cudaError_t linalg_init() {
     const char* e = getenv("GPB_RED");
     const int v = (e && e[0] == '0') ? 0 : 1;
     GPB_CK(cudaMemcpyToSymbol(g_red_epilogue, &v, sizeof(int)));
-    const char* d = getenv("GPB_DESYNC");
-    const int dc = d ? atoi(d) : 0;
-    GPB_CK(cudaMemcpyToSymbol(g_desync_cycles, &dc, sizeof(int)));
   }
   GPB_CK(set_smem_all<CfgBig>());
   GPB_CK(set_smem_all<CfgHalf>());
+  GPB_CK((set_smem<CfgQuarter, false, false, GeoSyrk>()));
+  GPB_CK((set_smem<CfgQuarter, false, false, GeoPanel>()));
   GPB_CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
   return cudaSuccess;
+}
+
+static bool quarter_tiles() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_QUARTER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 // outer panel width of the factorisation in 128-blocks.  Measured on B200 (potrf, ms, kb = 1 / 2): n = 4096 3.16 / 3.43,
@@ -593,13 +598,22 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     ++g_launches;
     return cudaGetLastError();
   };
+  // launches of the critical path that would not fill one wave with 64-row tiles use 32-row tiles: half the tile latency
+  auto small = [&](int rows) { return (long long)((rows + BM - 1) / BM) * B <= 160 && quarter_tiles(); };
   auto panel = [&](int k) -> cudaError_t {
-    const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
+    const int rows = nrows - (k + 1) * GPB_NB;
+    if (small(rows)) return launch_cfg<CfgQuarter, false, false>(GeoPanel{dm, k}, dim3((rows + 31) / 32, 1, B), ms);
+    const int Tm = (rows + BM - 1) / BM;
     return launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms);
   };
   auto syrk = [&](int kp, int kb, int c_lo, int c_hi, cudaStream_t st, bool bulk) -> cudaError_t {
     const int rows = nrows - (kp + kb) * GPB_NB;
     if (rows <= 0) return cudaSuccess;
+    if (!bulk && c_hi - c_lo == 1 && small(rows)) {
+      const int Tq = (rows + 31) / 32;
+      return launch_cfg<CfgQuarter, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi},
+                                                  dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false);
+    }
     const int Tm = (rows + BM - 1) / BM;
     return launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi},
                                          dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk);
