@@ -84,8 +84,18 @@ class HolisticCovarianceMatrix(CovarianceMatrix):
                 self._blocks = None
         if self._blocks is None:
             y = self.data_input.get_detrended_y_train()
-            self._blocks = DeviceBlocks([self.kernel], [self.data_input.data_x_train], [y], want_grad=True)
+            self._blocks = DeviceBlocks([self.kernel], [self.data_input.data_x_train], [y], want_grad=True,
+                                        grid=getattr(self, "_grid", None))
         return self._blocks
+
+    def distribute(self, grid):
+        """Factorise this ONE matrix over the processes of `grid` (engine.ProcessGrid; one process per GPU): distributed
+        Cholesky with NCCL panel broadcasts, inverse and trace gradient split by block column (csrc/dist.cu).  Every
+        rank must hold the same data and make the same calls in the same order; every rank gets the same NLL, gradient,
+        L and alpha.  BASELINE config 5 / SURVEY 8(e)."""
+        self._grid = grid
+        self._blocks = None
+        return self
 
     def nll_and_grad(self, hyper_parameter: List[torch.Tensor], noise, want_grad: bool = True):
         """(nll, [d nll / d hp], d nll / d noise) of the GP on the training data; grads are None without want_grad"""

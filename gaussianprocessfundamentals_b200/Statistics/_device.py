@@ -13,7 +13,8 @@ from ..program import flatten_hp, unflatten_grad
 class DeviceBlocks:
     """B independent (kernel, X, y) blocks evaluated as one batched plan."""
 
-    def __init__(self, kernels: Sequence, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], want_grad: bool = True):
+    def __init__(self, kernels: Sequence, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], want_grad: bool = True,
+                 grid=None):
         engine.require_cuda()
         self.kernels = list(kernels)
         self.ns = [int(x.shape[0]) for x in xs]
@@ -22,7 +23,7 @@ class DeviceBlocks:
         self.programs = [engine.DeviceProgram.get(kern.to_spec(), kern.get_dimensionality(), scaled, cp_mode)
                          for kern in self.kernels]
         self.key = (tuple(p.compiled.signature() for p in self.programs), tuple(self.ns), scaled, cp_mode, want_grad)
-        self.plan = engine.Plan(self.programs, self.ns, want_grad=want_grad)
+        self.plan = engine.Plan(self.programs, self.ns, want_grad=want_grad, grid=grid)
         self.want_grad = want_grad
         for b, (x, y) in enumerate(zip(xs, ys)):
             self.plan.set_data(b, x, y)

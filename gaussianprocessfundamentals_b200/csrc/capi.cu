@@ -324,7 +324,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
   p->ex.main = s;
   if (p->dist) {
-    if (stages & GPB_STAGE_BACKSOLVE) return fail_arg(2, "distributed plans do not implement BACKSOLVE");
+
     if (stages & GPB_STAGE_ASSEMBLE) {
       CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
       CU(gpb::run_assemble_batched(dm, 1, p->n_max, s), "assemble");
@@ -338,6 +338,8 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       }
     }
     if (stages & GPB_STAGE_NLL) CU(gpb::run_finalize_dist(dm, std::log(M_PI * 2.0), s), "finalize_dist");
+    // L and the inverted diagonal blocks are complete on every rank: the back substitution runs replicated
+    if (stages & GPB_STAGE_BACKSOLVE) CU(gpb::run_trsv(dm, 1, p->n_max, 1, s), "backsolve");
     auto dist_rc = [&](cudaError_t e, const char* where) -> int {
       if (e == cudaSuccess) return 0;
       if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }

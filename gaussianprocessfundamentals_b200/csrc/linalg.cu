@@ -187,14 +187,15 @@ struct GeoPlain {
 // element (n, n) behind y) is eliminated but never used as a pivot.
 constexpr int D_P = 264;                 // pitch of a panel buffer [8][D_P]: 256 rows per panel column
 constexpr int D_WLD = GPB_NB + 1;        // pitch of the transposing buffer of inv(L)
-constexpr int D_SLOTS = 34;              // register tiles per warp: 272 tiles / 8 warps
+// register tiles per warp: 272 tiles / NW warps (NW = 8: 34 tiles, 256 threads; NW = 16: 17 tiles, 512 threads)
 constexpr int D_SMEM_BYTES = (2 * 8 * D_P + GPB_NB * D_WLD + GPB_NB) * (int)sizeof(double);
 
-// tile L = 8 * slot + warp of the column-sorted list: column tj holds 16 - tj lower tiles of A, then tj + 1 upper tiles of X
+// tile L = NW * slot + warp of the column-sorted list: column tj holds 16 - tj lower tiles of A, then tj + 1 upper tiles of X
+template <int NW>
 __device__ __forceinline__ void diag_tile_of(int slot, int warp, int& ti, int& tj, bool& is_a) {
-  // slot is a compile-time constant at every call site: 8 * slot / 17 and the warp at which the column index steps
+  // slot is a compile-time constant at every call site: NW * slot / 17 and the warp at which the column index steps
   // fold to immediates, so the map costs a compare and two adds
-  const int base = 8 * slot, tj0 = base / 17, thr = 17 * (tj0 + 1) - base;
+  const int base = NW * slot, tj0 = base / 17, thr = 17 * (tj0 + 1) - base;
   const int L = base + warp;
   tj = tj0 + ((warp >= thr) ? 1 : 0);
   const int t = L - 17 * tj;
@@ -202,7 +203,10 @@ __device__ __forceinline__ void diag_tile_of(int slot, int warp, int& ti, int& t
   ti = is_a ? tj + t : t - (16 - tj);
 }
 
-__global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__ mats, int k) {
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 1) diag_kernel_t(const GpbMat* __restrict__ mats, int k) {
+  constexpr int D_SLOTS = 272 / NW;
+  constexpr int NT = 32 * NW;
   extern __shared__ __align__(16) double dsm[];
   double* Xs = dsm;                  // [8][D_P]  next panel column, row-per-thread order
   double* Ps = Xs + 8 * D_P;         // [8][D_P]  finished panel (DMMA operand)
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
 #pragma unroll
   for (int s = 0; s < D_SLOTS; ++s) {
     int ti, tj; bool is_a;
-    diag_tile_of(s, warp, ti, tj, is_a);
+    diag_tile_of<NW>(s, warp, ti, tj, is_a);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int row = ti * 8 + lr, col = tj * 8 + 2 * lk + e;
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
 #pragma unroll
   for (int s = 0; s < D_SLOTS; ++s) {
     int ti, tj; bool is_a;
-    diag_tile_of(s, warp, ti, tj, is_a);
+    diag_tile_of<NW>(s, warp, ti, tj, is_a);
     if (tj == 0) {
       const int rb = (is_a ? 0 : GPB_NB) + ti * 8 + lr;
       Xs[(2 * lk) * D_P + rb] = acc[s][0];
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
   for (int m = 0; m < nsteps; ++m) {
     // ---- (1) panel ------------------------------------------------------------------------------------------------
     const int c0 = 8 * m;
+    if (NW == 8 || warp < 8) {
     const bool active = a_row ? (R >= c0) : (xi < c0 + 8);
     double a[8], Dr[8];
 #pragma unroll
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
         Ws[(c0 + c) * D_WLD + xi] = v;                                   // inv(L)[c0 + c][xi] = X[xi][c0 + c]
       }
     }
+    }
     __syncthreads();
     // ---- (2) rank-8 update of the live tiles, publication of the next panel column -------------------------------
     if (m + 1 < nsteps) {
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (s0 + u < D_SLOTS) {
-            diag_tile_of(s0 + u, warp, ti[u], tj[u], is_a[u]);
+            diag_tile_of<NW>(s0 + u, warp, ti[u], tj[u], is_a[u]);
             act[u] = tj[u] > m && (is_a[u] || ti[u] <= m);
             any = any || act[u];
           }
@@ -364,10 +370,20 @@ __global__ void __launch_bounds__(256, 1) diag_kernel(const GpbMat* __restrict__
     if (s_info != 0 && *d.info == 0) *d.info = s_info;
   }
   double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
-  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += NT) {
     const int i = idx & (GPB_NB - 1), j = idx >> 7;
     Wg[idx] = (i >= j && i < bf) ? Ws[i * D_WLD + j] : 0.0;
   }
+}
+
+static int diag_warps() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_DIAG_WARPS"); v = (e && atoi(e) == 16) ? 16 : 8; }
+  return v;
+}
+static void launch_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
+  if (diag_warps() == 16) diag_kernel_t<16><<<B, 512, D_SMEM_BYTES, s>>>(dm, k);
+  else diag_kernel_t<8><<<B, 256, D_SMEM_BYTES, s>>>(dm, k);
 }
 
 // copy the inverted diagonal blocks into place (level 0 of the recursive-doubling inverse)
@@ -551,7 +567,8 @@ cudaError_t linalg_init() {
   GPB_CK(set_smem_all<CfgHalf>());
   GPB_CK((set_smem<CfgQuarter, false, false, GeoSyrk>()));
   GPB_CK((set_smem<CfgQuarter, false, false, GeoPanel>()));
-  GPB_CK(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
+  GPB_CK(cudaFuncSetAttribute(diag_kernel_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
+  GPB_CK(cudaFuncSetAttribute(diag_kernel_t<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
   return cudaSuccess;
 }
 
@@ -594,7 +611,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     return k < nblk && (k + 1) * GPB_NB <= n_max && nrows - (k + 1) * GPB_NB > 0;
   };
   auto diag = [&](int k) -> cudaError_t {
-    diag_kernel<<<B, 256, D_SMEM_BYTES, ms>>>(dm, k);
+    launch_diag(dm, B, k, ms);
     ++g_launches;
     return cudaGetLastError();
   };
@@ -664,7 +681,7 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
 }
 
 cudaError_t run_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
-  diag_kernel<<<B, 256, D_SMEM_BYTES, s>>>(dm, k);
+  launch_diag(dm, B, k, s);
   ++g_launches;
   return cudaGetLastError();
 }

@@ -219,3 +219,61 @@ def test_sharded_blockwise_likelihood_two_gpus():
         assert abs(v0 - v1) <= 1e-13 * abs(v0)
         assert np.allclose(g0, g1, rtol=1e-12, atol=0)
     assert got[0][1][True][0] == got[1][1][True][0]
+
+
+def _surface_worker(rank, world, port, out):
+    """the reference-shaped surface on a process grid: GaussianProcess -> LogLikelihood with covariance_matrix.distribute"""
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        from gaussianprocessfundamentals_b200 import engine as eng
+        from gaussianprocessfundamentals_b200.DataHandling import DataInput as di
+        from gaussianprocessfundamentals_b200.KernelBasics import BaseKernels as bk, Operators as op
+        from gaussianprocessfundamentals_b200.MeanFunctionBasics import BaseMeanFunctions as bmf
+        from gaussianprocessfundamentals_b200.Metrics import Auxiliary as met_aux, Metrics as met
+        from gaussianprocessfundamentals_b200.Statistics import GaussianProcess as gproc
+        n = 1500
+        rng = np.random.default_rng(5)
+        x = np.sort(rng.uniform(0, 1, size=(n, 1)), axis=0)
+        y = np.sin(11 * x) + 0.1 * rng.standard_normal((n, 1))
+        hp = [torch.tensor(0.15, dtype=torch.float64), torch.tensor(0.4, dtype=torch.float64),
+              torch.tensor(0.3, dtype=torch.float64)]
+        noise = torch.tensor(1e-2, dtype=torch.float64)
+        vals = {}
+        grid = eng.ProcessGrid(1, world)
+        for distributed in (False, True):
+            kern = op.AdditionOperator(1, [bk.SquaredExponentialKernel(1), bk.PeriodicKernel(1)])
+            din = di.DataInput(x, y, x[:50], y[:50])
+            din.set_mean_function(bmf.ZeroMeanFunction(1))
+            gp = gproc.GaussianProcess(kern, bmf.ZeroMeanFunction(1))
+            gp.set_data_input(din)
+            if distributed:
+                gp.covariance_matrix.distribute(grid)
+            metric = met_aux.get_metric_by_type(met.MetricType.LL, gp)
+            v = float(metric.get_metric(hp, noise, None))
+            g = np.concatenate([np.asarray(t).reshape(-1) for t in metric.get_gradients(hp, noise)])
+            gp.covariance_matrix.reset()
+            alpha = gp.covariance_matrix.get_L_alpha(hp, noise).cpu().numpy().reshape(-1)
+            vals[distributed] = (v, g, alpha)
+        dist.barrier()
+        out.put((rank, vals, None))
+        dist.destroy_process_group()
+    except Exception:
+        out.put((rank, None, traceback.format_exc()))
+
+
+@pytest.mark.timeout(600)
+def test_distributed_gp_through_the_reference_surface():
+    if _ngpu() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    got = _run(2, _surface_worker)
+    for rank, vals, _ in got:
+        v0, g0, a0 = vals[False]
+        v1, g1, a1 = vals[True]
+        assert abs(v0 - v1) <= LL_RTOL * abs(v0)
+        assert np.max(np.abs(g0 - g1)) <= GRAD_RTOL * np.max(np.abs(g0))
+        assert np.max(np.abs(a0 - a1)) <= 1e-9 * np.max(np.abs(a0))
+    assert got[0][1][True][0] == got[1][1][True][0]
