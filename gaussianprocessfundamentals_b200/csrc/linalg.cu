@@ -87,8 +87,10 @@ struct GeoTrtriT {
     const int r0 = 2 * s * b.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
-    const int tsn = s / BN;
-    const int ti = b.x / tsn, tj = b.x % tsn;
+    // column tile slowest and ascending: the k-range (tj*BN .. s) shrinks with tj, so the longest tiles start first and
+    // the launch drains with the short ones
+    const int tsm = s / BM;
+    const int ti = b.x % tsm, tj = b.x / tsm;
     if (ti * BM >= M) return false;
     const size_t ld = d.ld;
     J.A = d.A + (rA + ti * BM) + (size_t)r0 * ld;
@@ -112,8 +114,9 @@ struct GeoTrtriW {
     const int r0 = 2 * s * b.y, rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
-    const int tsn = s / BN;
-    const int ti = b.x / tsn, tj = b.x % tsn;
+    // row tile slowest and DEscending: the k-range (0 .. (ti+1)*BM) grows with ti, longest tiles first
+    const int tsn = s / BN, tsm = s / BM;
+    const int ti = tsm - 1 - (int)(b.x / tsn), tj = b.x % tsn;
     if (ti * BM >= M) return false;
     const size_t ld = d.ld;
     J.A = d.A + (rA + ti * BM) + (size_t)rA * ld;
