@@ -193,7 +193,7 @@ struct GeoDistPanel {
 // grid.y enumerates this rank's block columns of the range, grid.x the BM-row tiles from the diagonal block down.
 struct GeoDistSyrk {
   const GpbMat* mats;
-  int k, J_lo, J_hi, P, Q, p, q;
+  int k, kb, J_lo, J_hi, P, Q, p, q;     // panel = block columns k .. k + kb - 1 (kb = 1 or 2)
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "block columns are 128 wide");
@@ -213,7 +213,7 @@ struct GeoDistSyrk {
     J.lda = J.ldb = J.ldc = d.ld;
     J.mrem = min(BM, nrows - row);
     J.nrem = min(BN, nrows - Jb * GPB_NB);
-    J.klo = 0; J.khi = GPB_NB;
+    J.klo = 0; J.khi = kb * GPB_NB;
     J.alpha = -1.0; J.beta = 1.0; J.red = g_red_epilogue;
     return true;
   }
@@ -295,7 +295,8 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   GPB_CK(cudaStreamWaitEvent(cs, ex.ev_fork, 0));
   GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
   const size_t ld = h.ld;
-  for (int k = 0; k < nblk; ++k) {
+  // diagonal block k, its panel, and the exchange that leaves panel k (and inv(L_kk)) on every rank; all on the critical stream
+  auto factor_block = [&](int k) -> cudaError_t {
     const int qk = k % Q, pk = k % P;
     const int diag_owner = pk * Q + qk;
     const bool full = (k + 1) * GPB_NB <= n;               // full pivot block: a panel exists below it
@@ -357,23 +358,42 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
       ++g_launches;
       if (ship_wd && D.rank != diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd); ++g_launches; }
     }
-    if (!full) continue;
-    GPB_CK(cudaEventRecord(ex.ev_e[k & 1], cs));
-    // ---- trailing update: block column k+1 on the critical stream, k+2 first and then the rest on the side stream
-    const int J1 = k + 1, Jend = nbr;
-    auto syrk = [&](int Jlo, int Jhi, cudaStream_t s) -> cudaError_t {
-      if (Jhi > Jend) Jhi = Jend;
-      const int nc = count_owned_cols(Jlo, Jhi, Q, q);
-      if (nc == 0) return cudaSuccess;
-      const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
-      return launch_geo<Cfg>(GeoDistSyrk{dm, k, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true);
-    };
-    if (k > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(k - 1) & 1], 0));
-    GPB_CK(syrk(J1, J1 + 1, cs));
-    GPB_CK(cudaStreamWaitEvent(ss, ex.ev_e[k & 1], 0));
-    GPB_CK(syrk(J1 + 1, J1 + 2, ss));
-    GPB_CK(cudaEventRecord(ex.ev_g[k & 1], ss));
-    GPB_CK(syrk(J1 + 2, Jend, ss));
+    return cudaSuccess;
+  };
+  const int Jend = nbr;
+  auto syrk = [&](int kp, int kb, int Jlo, int Jhi, cudaStream_t s) -> cudaError_t {
+    if (Jhi > Jend) Jhi = Jend;
+    const int nc = count_owned_cols(Jlo, Jhi, Q, q);
+    if (nc == 0) return cudaSuccess;
+    const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
+    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true);
+  };
+  const bool wide = potrf_outer_blocks(n) > 1;             // 256-wide outer panels (two panels per far update)
+  int step = 0;
+  for (int k = 0; k < nblk;) {
+    GPB_CK(factor_block(k));
+    if ((k + 1) * GPB_NB > n) { ++k; continue; }           // last, partial block: no panel below it
+    int kb = 1;
+    bool waited = false;
+    if (wide && (k + 2) * GPB_NB <= n) {
+      // block column k+1 received its far update of the previous outer step on the side stream
+      if (step > 0) { GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(step - 1) & 1], 0)); waited = true; }
+      GPB_CK(syrk(k, 1, k + 1, k + 2, cs));                // strip: block column k+1 <- panel k
+      GPB_CK(factor_block(k + 1));
+      kb = 2;
+    }
+    GPB_CK(cudaEventRecord(ex.ev_e[step & 1], cs));
+    // ---- far update with both panels: the next diagonal column on the critical stream; on the side stream first the
+    //      columns the next outer step touches, then the rest
+    const int J1 = k + kb;
+    if (step > 0 && !waited) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(step - 1) & 1], 0));
+    GPB_CK(syrk(k, kb, J1, J1 + 1, cs));
+    GPB_CK(cudaStreamWaitEvent(ss, ex.ev_e[step & 1], 0));
+    GPB_CK(syrk(k, kb, J1 + 1, J1 + 1 + kb, ss));
+    GPB_CK(cudaEventRecord(ex.ev_g[step & 1], ss));
+    GPB_CK(syrk(k, kb, J1 + 1 + kb, Jend, ss));
+    k += kb;
+    ++step;
   }
   GPB_CK(cudaEventRecord(ex.ev_join[0], cs));
   GPB_CK(cudaEventRecord(ex.ev_join[1], ss));

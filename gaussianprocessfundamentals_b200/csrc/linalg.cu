@@ -599,6 +599,8 @@ static int kb_max(int n_max) {
 // the strip update of the second block column, and the first far column - runs on a high-priority stream so that its
 // few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream, which does
 // the columns the next outer step needs first and then the bulk.
+int potrf_outer_blocks(int n_max) { return kb_max(n_max); }
+
 template <class Cfg>
 static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
   constexpr int BM = Cfg::BM, R = Cfg::BN / Cfg::BM;
