@@ -437,24 +437,24 @@ struct GeoDistTriDiag {     // T_J = -Wd_I * X[I, J]      (out of place: X[I, J]
   }
 };
 
-struct GeoDistTriUpdate {   // X[r, J] += L[r, I] * X[I, J]  for r > I, J <= I own
+struct GeoDistTriUpdate {   // X[r, J] += L[r, I .. I+kb) * X[I .. I+kb, J]  for rows r in [row_lo, row_hi), own J < I + kb
   const GpbMat* mats;
-  int I, world, rank;
+  int I, kb, row_lo, row_hi, world, rank;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "block columns are 128 wide");
     const GpbMat& d = mats[0];
     const int Jb = rank + (int)b.y * world;
-    if (Jb > I) return false;
-    const int row = (I + 1) * GPB_NB + (int)b.x * BM;
-    if (row >= d.n) return false;
+    if (Jb > I + kb - 1) return false;
+    const int row = row_lo + (int)b.x * BM;
+    if (row >= row_hi) return false;
     const size_t ld = d.ld;
-    J.A = d.A + row + (size_t)I * GPB_NB * ld;                         // L[r, I], MN-major
-    J.B = d.Kinv + (size_t)I * GPB_NB + (size_t)Jb * GPB_NB * ld;      // X[I, J], K-major
-    J.C = d.Kinv + row + (size_t)Jb * GPB_NB * ld;
+    J.A = d.A + row + (size_t)I * GPB_NB * ld;                         // L[r, I..], MN-major
+    J.B = d.Kinv + (size_t)I * GPB_NB + (size_t)Jb * GPB_NB * ld;      // X[I.., J], K-major (rows above J's diagonal
+    J.C = d.Kinv + row + (size_t)Jb * GPB_NB * ld;                     //  block are the zeros of W)
     J.lda = J.ldb = J.ldc = d.ld;
-    J.mrem = min(BM, d.n - row); J.nrem = GPB_NB;
-    J.klo = 0; J.khi = GPB_NB;
+    J.mrem = min(BM, row_hi - row); J.nrem = GPB_NB;
+    J.klo = 0; J.khi = kb * GPB_NB;
     J.alpha = 1.0; J.beta = 1.0; J.red = g_red_epilogue;
     return true;
   }
@@ -528,17 +528,32 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     const int cols = std::min(GPB_NB, n - J * GPB_NB);
     GPB_CK(cudaMemsetAsync(h.Kinv + (size_t)J * GPB_NB * ld, 0, (size_t)cols * ld * sizeof(double), s));
   }
-  for (int I = 0; I < nblk; ++I) {
-    const int nJ_lt = own_cols_upto(I - 1, world, rank);     // own J < I
-    const int nJ_le = own_cols_upto(I, world, rank);         // own J <= I
-    if (nJ_le == 0) continue;
+  auto diag_solve = [&](int I) -> cudaError_t {            // X[I, J] <- -Wd_I X[I, J] (own J < I), X[I, I] <- Wd_I
+    const int nJ_lt = own_cols_upto(I - 1, world, rank);
+    const int nJ_le = own_cols_upto(I, world, rank);
+    if (nJ_le == 0) return cudaSuccess;
     if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), s)));
     tri_diag_store_kernel<<<nJ_le, 256, 0, s>>>(dm, scratch, I, world, rank);
     ++g_launches;
-    GPB_CK(cudaGetLastError());
-    const int rows = n - (I + 1) * GPB_NB;
-    if (rows > 0)
-      GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriUpdate{dm, I, world, rank}, dim3((rows + Cfg::BM - 1) / Cfg::BM, nJ_le, 1), s)));
+    return cudaGetLastError();
+  };
+  auto update = [&](int I, int kb, int row_lo, int row_hi) -> cudaError_t {
+    const int nJ = own_cols_upto(I + kb - 1, world, rank);
+    if (nJ == 0 || row_hi <= row_lo) return cudaSuccess;
+    return launch_geo2<Cfg, false, true>(GeoDistTriUpdate{dm, I, kb, row_lo, row_hi, world, rank},
+                                         dim3((row_hi - row_lo + Cfg::BM - 1) / Cfg::BM, nJ, 1), s);
+  };
+  const bool wide = potrf_outer_blocks(n) > 1;             // two block rows per far update (k = 256), as in the factorisation
+  for (int I = 0; I < nblk;) {
+    GPB_CK(diag_solve(I));
+    int kb = 1;
+    if (wide && (I + 2) * GPB_NB <= n) {
+      GPB_CK(update(I, 1, (I + 1) * GPB_NB, (I + 2) * GPB_NB));   // strip: block row I+1
+      GPB_CK(diag_solve(I + 1));
+      kb = 2;
+    }
+    GPB_CK(update(I, kb, (I + kb) * GPB_NB, n));
+    I += kb;
   }
   // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
   for (int J0 = 0; J0 < nblk; J0 += 64) {
