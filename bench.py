@@ -1,7 +1,8 @@
 """Benchmark of the exact-GP likelihood hot path (BASELINE.json: "LML+grad evals/sec at n=8k/32k FP64; FP64 TC % of
 peak in Cholesky").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|m32k|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|m32k|c1|c3|c4|c5|c5s|c5g|m32kd] [--grid PxQ]
 
 A step = one full LML + gradient evaluation (assembly -> Cholesky with carried y -> NLL -> inverse -> trace gradient)
 of the workload; default workload C2 = composite (SE+PER)xLIN kernel, n = 8192, d = 1.
@@ -11,6 +12,8 @@ of the workload; default workload C2 = composite (SE+PER)xLIN kernel, n = 8192, 
   N > 1  : C2 / M32k / C1 do not shard -> "replicas only": every rank evaluates its own replica, no collective
            (DESIGN.md); C3 / C4 (batched candidates / partition blocks) shard their GPs across ranks, no data-path
            collective either.  value = GP evaluations of all ranks / max-over-ranks time.
+           C5 / C5s (LML) and C5g / M32kd (LML + gradient) evaluate ONE matrix on all N GPUs: distributed Cholesky,
+           inverse and gradient with NCCL panel broadcasts (strong scaling; N = 1 is the single-GPU plan).
 --impl reference times the CPU restatement of the reference's unfused op sequence (oracle/gp_oracle.py, torch CPU,
 all host threads) on the same workload; TensorFlow - the reference's own engine - is not installable offline.
 """

@@ -266,6 +266,9 @@ size_t gpb_plan_workspace_bytes(const gpb_plan_t* plan) { return plan ? plan->ws
 int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
   if (!p) return fail_arg(1, "plan is null");
   if (!workspace || ((uintptr_t)workspace & 255)) return fail_arg(2, "workspace null or not 256-byte aligned");
+  // graphs captured for a previous workspace hold its addresses
+  for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);
+  p->n_graphs = 0;
   p->ws = (char*)workspace;
   std::vector<GpbMat> h(p->B);
   for (int b = 0; b < p->B; ++b) {

@@ -1,23 +1,29 @@
-// Distributed Cholesky / LML of ONE large GP over a P x Q process grid (one process per GPU, NCCL over NVLink).
+// One large GP over a P x Q process grid (one process per GPU, NCCL over NVLink / NVSwitch): distributed Cholesky,
+// triangular inverse, inv(K) and trace gradient.
 //
 // Replaces, for matrices too large or too slow for one GPU, the same reference calls as the single-GPU plan:
-// HolisticCovarianceMatrix.get_L_K / get_L_alpha (Statistics/CovarianceMatrix.py:247-265) and
-// LogLikelihood.get_metric (Metrics/LogLikelihood.py:30-65).  BASELINE config 5 / SURVEY 8(e), second row.
+// HolisticCovarianceMatrix.get_L_K / get_L_alpha (Statistics/CovarianceMatrix.py:247-265),
+// LogLikelihood.get_metric (Metrics/LogLikelihood.py:30-65) and the gradient of Optimizer/Fitter.py:124-158.
+// BASELINE config 5 / SURVEY 8(e), second row.
 //
-// Layout: 2D block-cyclic OWNERSHIP of the 128 x 128 blocks of the lower triangle - block (I, J) is assembled and
-// updated by rank (I mod P) * Q + (J mod Q) - over REPLICATED storage: every rank holds the full (n+1) x ld
+// Factorisation.  2D block-cyclic OWNERSHIP of the 128 x 128 blocks of the lower triangle - block (I, J) is assembled
+// and updated by rank (I mod P) * Q + (J mod Q) - over REPLICATED storage: every rank holds the full (n+1) x ld
 // column-major workspace of the single-GPU plan, its own blocks are live, and each finished panel (block column k of L)
-// is broadcast to all ranks, so that after the factorisation every rank holds the complete L (the later stages -
-// triangular solves, inverse, gradient - read all of it).  The exchange per step k is
-//   P == 1 : one ncclBroadcast of the packed panel (diagonal block + all blocks below it) from the column's owner
+// and inverted diagonal block is broadcast to all ranks, so that after the factorisation every rank holds the complete
+// L (the later stages read all of it).  The exchange per block column k is
+//   P == 1 : one grouped ncclBroadcast of the packed panel (diagonal block + all blocks below it) and inv(L_kk)
 //   P  > 1 : ncclBroadcast of {L_kk, inv(L_kk)} from the diagonal owner, then one grouped ncclBroadcast per process
 //            row of the panel blocks that row owns.
 // NVSwitch gives every pair of GPUs full bandwidth, so replicating the panel (n^2/2 doubles per rank over the whole
 // factorisation, 17 GB at n = 65536, ~25 ms at the measured 700 GB/s) is cheaper than the bookkeeping of row/column
-// communicators; the grid shape only balances the load.  Panels travel tile-major through two staging buffers.
+// communicators; the grid shape only balances the load (measured: 1 x N is fastest).  Panels travel tile-major through
+// two staging buffers.  Two panels are applied to the far trailing matrix together (k = 256) as on one GPU.
 //
-// Streams: the critical path (diagonal block, panel, exchange, update of the next block column) runs on the plan's
-// high-priority stream, the bulk of the trailing update on the low-priority one (look-ahead), exactly as on one GPU.
+// Streams: the critical path (diagonal block, panel, exchange, strip update, next diagonal column) runs on the plan's
+// high-priority stream, the bulk of the trailing update on the low-priority one (look-ahead).  CTAs of the bulk update
+// are one tile each: persistent CTAs kept every SM until the update ended and serialised the NCCL kernels behind it.
+//
+// Gradient stages: see the block comment above GeoDistTriDiag.
 #include <dlfcn.h>
 #include <cstdio>
 #include <algorithm>

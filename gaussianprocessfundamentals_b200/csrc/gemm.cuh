@@ -4,12 +4,11 @@
 //
 // C[BM x BN tile] = alpha * op(A) * op(B)^T + beta * C, FP64, DMMA.8x8x4 (mma.sync m8n8k4.f64).
 // Operands are staged with 16-byte cp.async (zero-filling out-of-range rows / k) into padded, bank-conflict-free
-// shared-memory tiles, 3 stages deep.  Two tile configurations share the code:
+// shared-memory tiles, 3 stages deep.  Three tile configurations share the code:
 //   CfgBig   128 x 128, 8 warps (4 x 2), warp tile 32 x 64, one CTA per SM
 //   CfgQuarter 32 x 128, 4 warps (1 x 4), warp tile 32 x 32, for launches smaller than one wave of CfgHalf tiles
 //   CfgHalf   64 x 128, 4 warps (2 x 2), warp tile 32 x 64, two CTAs per SM (the second CTA hides the first one's
-//             barrier / prologue / epilogue bubbles; twice as many CTAs for the single-wave launches of the
-//             factorisation's critical path)
+//             barrier / prologue / epilogue bubbles) - the default of every driver
 //
 // An operand is "MN-major" when element (mn, k) lives at P[mn + k*ld] (column-major op(A)=A) and "K-major" when it
 // lives at P[k + mn*ld] (column-major op(A)=A^T); both are supported for A and B so that NT / NN / TN products of

@@ -113,15 +113,18 @@ void gpb_plan_destroy(gpb_plan_t* plan);
 
 /* ---- one large GP over a process grid (one process per GPU; NCCL over NVLink / NVSwitch) --------------------
  * Replaces the same reference calls as a B = 1 plan (HolisticCovarianceMatrix.get_L_K / get_L_alpha,
- * Statistics/CovarianceMatrix.py:247-265; LogLikelihood.get_metric, Metrics/LogLikelihood.py:30-65) when one matrix
- * is factorised by several GPUs: the 128 x 128 blocks of the lower triangle are owned 2D block-cyclically, block (I, J)
- * by rank (I mod P) * Q + (J mod Q); every finished panel is broadcast (ncclBroadcast), so all ranks end up with the
- * complete factor L, z = L^-1 y and the same nll / info.  libnccl.so.2 is bound at run time by gpb_dist_unique_id /
- * gpb_dist_init only.
+ * Statistics/CovarianceMatrix.py:247-265; LogLikelihood.get_metric, Metrics/LogLikelihood.py:30-65; the gradient of
+ * Optimizer/Fitter.py:124-158) when one matrix is evaluated by several GPUs.
+ *   factorisation : the 128 x 128 blocks of the lower triangle are owned 2D block-cyclically, block (I, J) by rank
+ *                   (I mod P) * Q + (J mod Q); every finished panel and inverted diagonal block is broadcast
+ *                   (ncclBroadcast), so all ranks end up with the complete factor L, z = L^-1 y and the same nll / info
+ *   gradient      : W = L^-1, K^-1 = W^T W and the trace gradient are split by block column (J mod world), with one
+ *                   exchange of W and one ncclAllReduce of the n_hp + 1 gradient entries; every rank gets the same grad
+ * libnccl.so.2 is bound at run time by gpb_dist_unique_id / gpb_dist_init only.
  *   rank 0 calls gpb_dist_unique_id and ships the 128 bytes to the other ranks with the host's own transport;
  *   every rank then calls gpb_dist_init (collective), creates the plan with gpb_plan_create_dist, binds a workspace,
- *   fills the SAME X / y / hp / noise into the plan's buffers and calls gpb_plan_eval / gpb_plan_eval_host with
- *   stages from ASSEMBLE | POTRF | NLL (collective: every rank must make the same calls in the same order).       */
+ *   fills the SAME X / y / hp / noise into the plan's buffers and calls gpb_plan_eval / gpb_plan_eval_host with any
+ *   stage mask (collective: every rank must make the same calls in the same order).                              */
 int gpb_dist_unique_id(unsigned char* id128);
 int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q, gpb_dist_t** out);
 void gpb_dist_destroy(gpb_dist_t* dist);
