@@ -184,3 +184,26 @@ def test_sharded_blockwise_nll_two_ranks_gloo():
         assert val == pytest.approx(want_val, rel=1e-14)
         assert np.allclose(flat, want_flat, rtol=1e-13, atol=0)
     assert sorted(got[0][4][0] + got[1][4][0]) == sorted(active_sizes)
+
+
+# ---- bench.py's own sharding of the batched workloads -----------------------------------------------------------
+def test_bench_workloads_partition_their_gps_across_ranks():
+    """C3 / C4 of bench.py: every GP is evaluated by exactly one rank, whatever the number of ranks, and a rank's share is
+    the same data it would hold in the single-process run (build_workload is pure host code)."""
+    import bench
+    for key, B in (("c3", 256), ("c4", 1024)):
+        t1, h1, n1, x1, y1 = bench.build_workload(key, 0, 1)
+        assert len(t1) == B and all(n == bench.WORKLOADS[key]["n"] for n in n1)
+        for world in (2, 8):
+            seen = []
+            for rank in range(world):
+                t, h, ns, xs, ys = bench.build_workload(key, rank, world)
+                mine = list(range(rank, B, world))
+                assert len(t) == len(mine)
+                seen += mine
+                for pos in (0, len(mine) - 1):                      # spot-check: same tree, hyper-parameters and targets
+                    b = mine[pos]
+                    assert t[pos] == t1[b]
+                    assert np.array_equal(h[pos], h1[b])
+                    assert np.array_equal(ys[pos], y1[b]) and np.array_equal(xs[pos], x1[b])
+            assert sorted(seen) == list(range(B))
