@@ -1,6 +1,7 @@
 """GPU parity tests of the CUDA path (through the C-ABI) against the CPU oracle.  Tolerances (north_star):
 relative <= 1e-10 on the log-likelihood, <= 1e-8 on gradients; matrices element-wise to a few ulp."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -9,6 +10,8 @@ import torch
 from oracle import gp_oracle as orc
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 LL_RTOL = 1e-10
 GRAD_RTOL = 1e-8
@@ -289,3 +292,39 @@ def test_large_roundtrip_properties():
     Kinv = Kl + torch.tril(Kl, -1).t()
     r2 = Kinv @ (Kfull @ v) - v
     assert float(r2.abs().max()) <= 1e-6 * float(v.abs().max())
+
+
+def test_wide_outer_panels_on_ragged_batches_subprocess():
+    """The 256-wide outer panels of the Cholesky driver are chosen for n >= 6144 only; GPB_POTRF_KB=2 (read once per
+    process) forces them, so a subprocess evaluates a ragged batch - sizes on both sides of block boundaries, odd and
+    even numbers of blocks - against the oracle with the wide panels on."""
+    import subprocess
+    import sys
+    script = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from gaussianprocessfundamentals_b200 import engine as eng
+from oracle import gp_oracle as orc
+tree = ("ADD", [("SE",), ("PER",)])
+hp = np.array([0.2, 0.5, 0.3])
+ns = [700, 640, 513, 384, 1000, 129, 257, 256]
+prog = eng.DeviceProgram.get(tree, 1, False, 1)
+plan = eng.Plan([prog] * len(ns), ns, want_grad=True)
+data = []
+for b, n in enumerate(ns):
+    rng = np.random.default_rng(50 + b)
+    x = np.sort(rng.uniform(0, 1, (n, 1)), axis=0); y = np.sin(7 * x) + 0.1 * rng.standard_normal((n, 1))
+    data.append((x, y)); plan.set_data(b, torch.tensor(x), torch.tensor(y)); plan.set_hp(b, hp, 1e-2)
+plan.eval(eng.STAGES_LML_GRAD); torch.cuda.synchronize()
+nll, grads, info = plan.results()
+assert int(np.max(info)) == 0
+for b, n in enumerate(ns):
+    want, g, gn = orc.nll_and_grad(tree, [np.asarray(v) for v in hp], 1e-2, data[b][0], data[b][1], reference_distance=False)
+    assert abs(nll[b] - want) <= 1e-10 * abs(want), (n, nll[b], want)
+    gw = np.concatenate([np.asarray(t).reshape(-1) for t in g] + [[gn]])
+    assert np.max(np.abs(grads[b] - gw)) <= 1e-8 * np.max(np.abs(gw)), (n, grads[b], gw)
+print("ok")
+""" % ROOT
+    env = dict(os.environ, GPB_POTRF_KB="2")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr

@@ -141,10 +141,18 @@ def _run(world, target, *args):
 
 
 @pytest.mark.timeout(900)
-def test_distributed_cholesky_matches_single_gpu():
+@pytest.mark.parametrize("outer_blocks", ["", "2"])
+def test_distributed_cholesky_matches_single_gpu(outer_blocks, monkeypatch):
+    """outer_blocks = "2" forces the 256-wide outer panels (two panels / two block rows per far update) that the drivers
+    only choose for n >= 6144, so that the test sizes exercise them too (GPB_POTRF_KB is read once per process; the
+    spawned ranks inherit it)."""
     world = min(_ngpu(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
+    if outer_blocks:
+        monkeypatch.setenv("GPB_POTRF_KB", outer_blocks)
+    else:
+        monkeypatch.delenv("GPB_POTRF_KB", raising=False)
     world = 4 if world >= 4 else 2
     shapes = [(1, 2), (2, 1)] if world == 2 else [(1, 4), (2, 2), (4, 1)]
     cases = []
