@@ -273,28 +273,38 @@ __global__ void __launch_bounds__(32 * NW, 1) diag_kernel_t(const GpbMat* __rest
       Dr[c] = (lane < 8) ? Xs[c * D_P + c0 + lane] : 0.0;
     }
     const int npiv = min(8, max(0, bf - c0));
+    // Software-pipelined pivot chain: as soon as column c+1 has received the update of pivot c, its pivot is broadcast
+    // and the reciprocal square root of the NEXT pivot is started, so that its latency runs under the updates of the
+    // columns c+2.. .  Branch-free (selects) so that the compiler keeps this order: rsqrt of a non-pivot is discarded.
+    double dv = __shfl_sync(0xffffffffu, Dr[0], 0);
+    double inv = (0 < npiv) ? rsqrt(dv) : 1.0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const double dv = __shfl_sync(0xffffffffu, Dr[c], c);
-      double inv = 1.0, lcc = dv;
-      if (c < npiv) {
-        if (!(dv > 0.0) && tid == 0 && s_info == 0) s_info = r0 + c0 + c + 1;
-        // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_cc = d * rsqrt(d): a third of the latency of
-        // sqrt followed by a division on the one chain of the factorisation that cannot be parallelised
-        inv = rsqrt(dv);
-        lcc = dv * inv;
-        if (warp == 7 && lane == c) piv[c0 + c] = lcc;
-      }
+      // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_cc = d * rsqrt(d): a third of the latency of
+      // sqrt followed by a division on the one chain of the factorisation that cannot be parallelised
+      const bool is_piv = c < npiv;
+      const double lcc = is_piv ? dv * inv : dv;
+      if (is_piv && !(dv > 0.0) && tid == 0 && s_info == 0) s_info = r0 + c0 + c + 1;
+      if (is_piv && warp == 7 && lane == c) piv[c0 + c] = lcc;
       const double li = Dr[c] * inv;       // lane i > c: L[i][c] of the micro-block
       double xc = a[c] * inv;
       if (a_row && R - c0 == c) xc = lcc;  // the diagonal element itself
+      double dv_n = 0.0, inv_n = 1.0;
+      if (c + 1 < 8) {
+        const double l = __shfl_sync(0xffffffffu, li, c + 1);
+        Dr[c + 1] = fma(-li, l, Dr[c + 1]);
+        a[c + 1] = fma(-xc, l, a[c + 1]);
+        dv_n = __shfl_sync(0xffffffffu, Dr[c + 1], c + 1);
+        inv_n = (c + 1 < npiv) ? rsqrt(dv_n) : 1.0;
+      }
 #pragma unroll
-      for (int c2 = c + 1; c2 < 8; ++c2) {
+      for (int c2 = c + 2; c2 < 8; ++c2) {
         const double l = __shfl_sync(0xffffffffu, li, c2);   // L[c2][c]
         Dr[c2] = fma(-li, l, Dr[c2]);
         a[c2] = fma(-xc, l, a[c2]);
       }
       a[c] = xc;
+      dv = dv_n; inv = inv_n;
     }
     // rows of the micro-block itself: zero above the diagonal (those entries of the symmetric block were never loaded)
     if (a_row && R >= c0 && R < c0 + 8) {
