@@ -177,5 +177,82 @@ class AdamFitter(Fitter):
         return pre_fit_metric, post_fit_metric, kernel.get_last_hyper_parameter(), kernel.get_noise(), None
 
 
+class LbfgsFitter(Fitter):
+    """Quasi-Newton fit loop: L-BFGS-B over the flat hyper-parameter vector, every function / gradient
+    evaluation one fused device evaluation (assembly, Cholesky with carried y, inverse, trace gradient).  Box constraints
+    are the kernel's own `get_hyper_parameter_bounds` when `p_check_hyper_parameters` is set (the reference only uses
+    them to replace gradients, Fitter.py:122-152); a non positive-definite trial point is reported to the line search
+    as +inf instead of aborting the fit."""
+
+    def __init__(self, data_input, gaussian_process, metric_type: met.MetricType, from_distribution: bool, local_approx,
+                 numerical_matrix_handling, subset_size: int = None, max_evaluations: int = 60, tolerance: float = 1e-9):
+        super().__init__(data_input, gaussian_process, metric_type, ft.FitterType.GRADIENT, from_distribution,
+                         local_approx, numerical_matrix_handling, subset_size)
+        self.max_evaluations, self.tolerance = int(max_evaluations), float(tolerance)
+        self.history: List[float] = []
+        self.result = None
+
+    @staticmethod
+    def _flatten(variables):
+        import numpy as np
+        return np.concatenate([v.detach().cpu().numpy().reshape(-1) for v in variables]).astype("float64")
+
+    @staticmethod
+    def _unflatten(flat, like):
+        out, pos = [], 0
+        for v in like:
+            k = v.numel()
+            out.append(torch.as_tensor(flat[pos:pos + k], dtype=torch.float64).reshape(v.shape).clone())
+            pos += k
+        return out
+
+    def _flat_bounds(self, variables, xrange, n):
+        """(lo, hi) per scalar, or None; the raw noise (p_optimize_noise) is unbounded"""
+        if not global_param.p_check_hyper_parameters:
+            return None
+        import numpy as np
+        bounds = []
+        if global_param.p_optimize_noise:
+            bounds.append((None, None))
+        for (lo, hi), v in zip(self._gp.kernel.get_hyper_parameter_bounds(xrange, n),
+                               variables[1:] if global_param.p_optimize_noise else variables):
+            lo = np.broadcast_to(np.asarray(lo, dtype="float64"), tuple(v.shape)).reshape(-1)
+            hi = np.broadcast_to(np.asarray(hi, dtype="float64"), tuple(v.shape)).reshape(-1)
+            for a, b in zip(lo, hi):
+                a, b = (None if not np.isfinite(a) else float(a)), (None if not np.isfinite(b) else float(b))
+                if a is not None and b is not None and a > b:
+                    a, b = None, None          # the reference's log-scaled period bounds can be inverted (SURVEY App. A)
+                bounds.append((a, b))
+        return bounds
+
+    def fit(self):
+        import numpy as np
+        from scipy.optimize import minimize
+        variables, xrange, n = self._initial_variables()
+        pre_fit_metric = self._metric_value(variables)
+        self.history = []
+
+        def fun(flat):
+            trial = self._unflatten(flat, variables)
+            try:
+                value, grads = self._objective(trial)
+            except ArithmeticError:            # engine.NotPositiveDefinite: let the line search back off
+                return np.inf, np.zeros_like(flat)
+            self.history.append(float(value))
+            g = np.concatenate([np.asarray(t, dtype="float64").reshape(-1) for t in grads])
+            if not np.isfinite(value) or not np.all(np.isfinite(g)):
+                return np.inf, np.zeros_like(flat)
+            return float(value), g
+
+        self.result = minimize(fun, self._flatten(variables), jac=True, method="L-BFGS-B",
+                               bounds=self._flat_bounds(variables, xrange, n),
+                               options={"maxfun": self.max_evaluations, "ftol": self.tolerance, "gtol": 1e-10})
+        best = self._unflatten(self.result.x, variables)
+        self._store(best)
+        post_fit_metric = self._metric_value(best)
+        kernel = self._gp.covariance_matrix.kernel
+        return pre_fit_metric, post_fit_metric, kernel.get_last_hyper_parameter(), kernel.get_noise(), None
+
+
 if global_param.p_gradient_fitter is None:
     global_param.p_gradient_fitter = VariationalSgdFitter

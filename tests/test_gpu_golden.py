@@ -262,6 +262,18 @@ def test_autograd_bridge_and_adam_fit_loop(gpb):
     finally:
         g.global_param.p_cov_matrix_jitter = torch.tensor(1e-8, dtype=torch.float64)
     assert float(post) < float(pre)
+    # quasi-Newton loop on the same problem: must reach a lower NLL than 25 Adam steps, in few evaluations
+    g.global_param.p_cov_matrix_jitter = torch.tensor(0.05, dtype=torch.float64)
+    try:
+        f2 = g.fitter.LbfgsFitter(din, g.gproc.GaussianProcess(kern, g.bmf.ZeroMeanFunction(1)), g.met.MetricType.LL, False,
+                                  g.mht.MatrixApproximations.NONE, g.mht.NumericalMatrixHandlingType.CHOLESKY_BASED,
+                                  max_evaluations=40)
+        pre2, post2, hps2, nz2, _ = f2.fit()
+    finally:
+        g.global_param.p_cov_matrix_jitter = torch.tensor(1e-8, dtype=torch.float64)
+    assert float(post2) <= float(post) + 1e-9 and len(f2.history) <= 41
+    gfin = metric.get_gradients([torch.as_tensor(h) for h in hps2], torch.tensor(0.05, dtype=torch.float64))
+    assert max(float(torch.as_tensor(t).abs().max()) for t in gfin) <= 1e-2 * max(1.0, abs(float(post2)))
 
 
 def test_distances_and_prediction(gpb):

@@ -198,3 +198,48 @@ def test_distributed_layout_host_arithmetic():
                 assert sorted(slots.values()) == list(range(nt))
     assert lib.gpb_dist_owner(-1, 0, 1, 1) == -1
     assert lib.gpb_dist_panel_segments(0, 4, 9, base, cnt, first) != 0      # P > 8 is refused
+
+
+def test_lbfgs_fitter_host_logic_without_device(monkeypatch):
+    """LbfgsFitter's host side - flatten / unflatten of the hyper-parameter list, bounds from the kernel, a non-PD trial
+    point reported as +inf, best point stored on the kernel - with the device objective replaced by a quadratic."""
+    from gaussianprocessfundamentals_b200.Optimizer import Fitter as fitter
+    from gaussianprocessfundamentals_b200 import global_parameters as gparam
+
+    kern = op.AdditionOperator(1, [bk.SquaredExponentialKernel(1), bk.LinearKernel(1)])
+    f = fitter.LbfgsFitter.__new__(fitter.LbfgsFitter)
+    f.max_evaluations, f.tolerance, f.history, f.result = 50, 1e-12, [], None
+
+    class _Cov:
+        kernel = kern
+    class _Gp:
+        covariance_matrix = _Cov()
+    _Gp.kernel = kern
+    f._gp = _Gp()
+    target = [torch.tensor(0.3, dtype=torch.float64), torch.tensor([0.7], dtype=torch.float64)]
+    calls = {"n": 0}
+
+    def objective(variables):
+        calls["n"] += 1
+        if float(variables[0]) > 5.0:
+            raise ArithmeticError("not positive definite")
+        val = sum(float(((v - t) ** 2).sum()) for v, t in zip(variables, target))
+        return val, [2 * (v - t) for v, t in zip(variables, target)]
+
+    f._objective = objective
+    f._metric_value = lambda variables: torch.tensor([[objective(variables)[0]]], dtype=torch.float64)
+    f._initial_variables = lambda: ([torch.tensor(1.0, dtype=torch.float64), torch.tensor([0.01], dtype=torch.float64)],
+                                    [[0.0, 1.0]], 100)
+    monkeypatch.setattr(gparam, "p_check_hyper_parameters", False)
+    monkeypatch.setattr(gparam, "p_optimize_noise", False)
+    pre, post, hps, noise, _ = f.fit()
+    assert float(post) < 1e-12 < float(pre)
+    assert abs(float(torch.as_tensor(hps[0])) - 0.3) < 1e-6 and abs(float(torch.as_tensor(hps[1]).reshape(-1)[0]) - 0.7) < 1e-6
+    assert [tuple(torch.as_tensor(h).shape) for h in hps] == [(), (1,)]
+    # bounds: lengthscale in [5 R / n, R / 3] = [0.05, 1/3]; the linear offset is unbounded
+    monkeypatch.setattr(gparam, "p_check_hyper_parameters", True)
+    b = f._flat_bounds(f._initial_variables()[0], [[0.0, 1.0]], 100)
+    assert b[0][0] == pytest.approx(0.05) and b[0][1] == pytest.approx(1.0 / 3.0) and b[1] == (None, None)
+    target[0] = torch.tensor(2.0, dtype=torch.float64)           # optimum outside the box: the fit stops at the bound
+    pre, post, hps, noise, _ = f.fit()
+    assert abs(float(torch.as_tensor(hps[0])) - 1.0 / 3.0) < 1e-9
