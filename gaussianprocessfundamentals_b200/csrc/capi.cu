@@ -230,11 +230,13 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.crit, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.side, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.inv, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&p->ex.ev_e[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_g[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_c[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
   p->n_graphs = 0; p->graphs_off = 0; p->gstream = nullptr;
   {
@@ -368,9 +370,15 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, (size_t)p->B * 4, s), "reset info");
     CU(gpb::run_assemble_batched(dm, p->B, p->n_max, s), "assemble");
   }
+  // one large matrix, factorisation and inverse in the same call: the inverse of the block columns that are already
+  // final runs under the factorisation's latency-bound tail (GPB_FUSE_TRTRI=0 keeps the stages apart)
+  bool fused_trtri = false;
   if (stages & GPB_STAGE_POTRF) {
     const bool lookahead = (p->B == 1 && p->n_max >= 1024);
-    CU(gpb::run_potrf(dm, p->B, p->n_max, 1, lookahead, p->ex), "potrf");
+    static int fuse_env = -1;
+    if (fuse_env < 0) { const char* fe = getenv("GPB_FUSE_TRTRI"); fuse_env = (fe && fe[0] == '0') ? 0 : 1; }
+    fused_trtri = lookahead && fuse_env && (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) != 0;
+    CU(gpb::run_potrf(dm, p->B, p->n_max, 1, lookahead, fused_trtri, p->ex), "potrf");
   }
   if (stages & GPB_STAGE_NLL) {
     const double log2pi = std::log(M_PI * 2.0);
@@ -378,7 +386,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   }
   if (stages & GPB_STAGE_BACKSOLVE) CU(gpb::run_trsv(dm, p->B, p->n_max, 1, s), "backsolve");
   if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
-    CU(gpb::run_trtri(dm, p->B, p->n_max, s), "trtri");
+    if (!fused_trtri) CU(gpb::run_trtri(dm, p->B, p->n_max, s), "trtri");
     CU(gpb::run_alpha(dm, p->B, p->n_max, s), "alpha");
   }
   if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
@@ -452,9 +460,11 @@ void gpb_plan_destroy(gpb_plan_t* p) {
   if (p->own_streams) {
     cudaStreamDestroy(p->ex.crit);
     cudaStreamDestroy(p->ex.side);
+    cudaStreamDestroy(p->ex.inv);
     for (int i = 0; i < 2; ++i) {
-      cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_join[i]);
+      cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_c[i]);
     }
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(p->ex.ev_join[i]);
     cudaEventDestroy(p->ex.ev_fork);
     for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);
     if (p->gstream) { cudaStreamDestroy(p->gstream); cudaEventDestroy(p->g_in); cudaEventDestroy(p->g_out); }

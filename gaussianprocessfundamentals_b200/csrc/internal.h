@@ -13,14 +13,17 @@ struct Exec {
   cudaStream_t main;       // the caller's stream
   cudaStream_t crit;       // high priority: diagonal block, panel, next panel column (the critical path)
   cudaStream_t side;       // low priority: the bulk of the trailing update
+  cudaStream_t inv;        // low priority: the triangular inverse of what is already final (overlapped with the tail)
+  cudaEvent_t ev_c[2];     // block columns final (recorded on crit, waited on by inv)
   cudaEvent_t ev_fork;     // caller's stream -> crit / side
   cudaEvent_t ev_e[2];     // panel k ready (recorded on crit)
   cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side)
-  cudaEvent_t ev_join[2];  // crit / side -> caller's stream
+  cudaEvent_t ev_join[3];  // crit / side / inv -> caller's stream
 };
 
 // ---- linalg.cu ------------------------------------------------------------------------------------------------
-cudaError_t run_potrf(const GpbMat* dmats, int B, int n_max, int aug, bool lookahead, const Exec& ex);
+// with_trtri: also compute W = inv(L) in place, overlapped with the factorisation (look-ahead path, B == 1)
+cudaError_t run_potrf(const GpbMat* dmats, int B, int n_max, int aug, bool lookahead, bool with_trtri, const Exec& ex);
 cudaError_t run_diag(const GpbMat* dmats, int B, int k, cudaStream_t s);   // diagonal block k: Cholesky + inverse
 cudaError_t run_finalize(const GpbMat* dmats, int B, double log2pi, cudaStream_t s);
 cudaError_t run_trtri(const GpbMat* dmats, int B, int n_max, cudaStream_t s);

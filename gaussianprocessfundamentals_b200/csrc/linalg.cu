@@ -80,11 +80,11 @@ struct GeoPanel {
 // phase T:  T = L21 * W11   (NN, k >= tile column start because W11 is lower triangular)   -> Kinv scratch
 struct GeoTrtriT {
   const GpbMat* mats;
-  int s;
+  int s, p0;   // sub-problems p0, p0 + 1, ... (grid.y of them)
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
-    const int r0 = 2 * s * b.y, rA = r0 + s;
+    const int r0 = 2 * s * ((int)b.y + p0), rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
     // column tile slowest and ascending: the k-range (tj*BN .. s) shrinks with tj, so the longest tiles start first and
@@ -107,11 +107,11 @@ struct GeoTrtriT {
 // phase W:  W21 = -W22 * T   (NN, k <= tile row end because W22 is lower triangular)
 struct GeoTrtriW {
   const GpbMat* mats;
-  int s;
+  int s, p0;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
-    const int r0 = 2 * s * b.y, rA = r0 + s;
+    const int r0 = 2 * s * ((int)b.y + p0), rA = r0 + s;
     if (rA >= d.n) return false;
     const int M = min(s, d.n - rA);
     // row tile slowest and DEscending: the k-range (0 .. (ti+1)*BM) grows with ti, longest tiles first
@@ -400,9 +400,9 @@ static void launch_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
 }
 
 // copy the inverted diagonal blocks into place (level 0 of the recursive-doubling inverse)
-__global__ void diag_copy_kernel(const GpbMat* __restrict__ mats) {
+__global__ void diag_copy_kernel(const GpbMat* __restrict__ mats, int k0) {
   const GpbMat d = mats[blockIdx.y];
-  const int k = blockIdx.x;
+  const int k = blockIdx.x + k0;
   const int r0 = k * GPB_NB;
   if (r0 >= d.n) return;
   const int bf = min(GPB_NB, d.n - r0);
@@ -611,8 +611,88 @@ static int kb_max(int n_max) {
 // the columns the next outer step needs first and then the bulk.
 int potrf_outer_blocks(int n_max) { return kb_max(n_max); }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Triangular inverse overlapped with the factorisation (one large matrix).  The recursive-doubling inverse is a task
+// graph: level s, sub-problem p needs only the block columns of L left of its own end, and a block column of L is final
+// as soon as its panel is solved.  So while the factorisation's tail is bound by its serial chain (diagonal block ->
+// panel -> column) and leaves most SMs idle, the inverse of everything already final runs on a third, low-priority
+// stream.  Readiness (fc = number of final columns):
+//   T(s, p) : T = L21 W11      needs columns [r0, rA) final and every lower-level task left of rA launched
+//   W(s, p) : W21 = -W22 T     needs columns up to the sub-problem's end final, T(s, p) and every lower-level task left
+//                              of that end launched
+// Tasks are launched in level order on ONE stream, so "launched" implies "ordered before".  A W task overwrites
+// L21 inside its own diagonal block only, i.e. rows above fc, which no later step of the factorisation reads.
+// ---------------------------------------------------------------------------------------------------------------
+struct TrtriSched {
+  int n = 0, nblk = 0, nlev = 0, copied = 0;
+  int nextT[24], nextW[24], nsub[24];
+  void init(int n_) {
+    n = n_; nblk = (n + GPB_NB - 1) / GPB_NB; nlev = 0; copied = 0;
+    for (long long s = GPB_NB; s < n && nlev < 24; s *= 2) {
+      nsub[nlev] = (int)((n - s + 2 * s - 1) / (2 * s));   // sub-problems with rA = 2 s p + s < n
+      nextT[nlev] = nextW[nlev] = 0;
+      ++nlev;
+    }
+  }
+  bool lower_done(int li, long long X) const {            // everything below level li that starts left of X is launched
+    const long long Xc = X < n ? X : n;
+    if (copied < (int)((Xc + GPB_NB - 1) / GPB_NB)) return false;
+    for (int lj = 0; lj < li; ++lj) {
+      const long long s2 = 2LL * (GPB_NB << lj);
+      long long need = (X + s2 - 1) / s2;
+      if (need > nsub[lj]) need = nsub[lj];
+      if (nextW[lj] < need) return false;
+    }
+    return true;
+  }
+  bool finished() const {
+    if (copied < nblk) return false;
+    for (int li = 0; li < nlev; ++li) if (nextW[li] < nsub[li]) return false;
+    return true;
+  }
+  template <class Cfg>
+  cudaError_t advance(const GpbMat* dm, long long fc, cudaStream_t st) {
+    bool progress = true;
+    while (progress) {
+      progress = false;
+      const int newc = fc >= n ? nblk : (int)(fc / GPB_NB);
+      if (newc > copied) {
+        diag_copy_kernel<<<dim3(newc - copied, 1), 256, 0, st>>>(dm, copied);
+        ++g_launches;
+        GPB_CK(cudaGetLastError());
+        copied = newc; progress = true;
+      }
+      for (int li = 0; li < nlev; ++li) {
+        const long long s = (long long)GPB_NB << li;
+        const int tiles = (int)(s / Cfg::BM) * (int)(s / Cfg::BN);
+        int cnt = 0;
+        while (nextT[li] + cnt < nsub[li]) {
+          const long long rA = 2 * s * (nextT[li] + cnt) + s;
+          if (rA <= fc && lower_done(li, rA)) ++cnt; else break;
+        }
+        if (cnt) {
+          GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriT{dm, (int)s, nextT[li]}, dim3(tiles, cnt, 1), st)));
+          nextT[li] += cnt; progress = true;
+        }
+        cnt = 0;
+        while (nextW[li] + cnt < nextT[li]) {
+          const long long end = 2 * s * (nextW[li] + cnt + 1);
+          if ((end < n ? end : n) <= fc && lower_done(li, end)) ++cnt; else break;
+        }
+        if (cnt) {
+          GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriW{dm, (int)s, nextW[li]}, dim3(tiles, cnt, 1), st)));
+          nextW[li] += cnt; progress = true;
+        }
+      }
+    }
+    return cudaSuccess;
+  }
+};
+
+
 template <class Cfg>
-static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
+static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, bool with_trtri,
+                              const Exec& ex) {
   constexpr int BM = Cfg::BM, R = Cfg::BN / Cfg::BM;
   const int nrows = n_max + aug;
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
@@ -622,6 +702,19 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     GPB_CK(cudaStreamWaitEvent(ex.crit, ex.ev_fork, 0));
     GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_fork, 0));
   }
+  const bool fuse = lookahead && with_trtri && B == 1;
+  TrtriSched sched;
+  if (fuse) { sched.init(n_max); GPB_CK(cudaStreamWaitEvent(ex.inv, ex.ev_fork, 0)); }
+  int n_adv = 0;
+  // block columns [0, kc) of L are final on stream ms at this point: hand everything that became invertible to ex.inv
+  auto inverse_progress = [&](int kc) -> cudaError_t {
+    if (!fuse) return cudaSuccess;
+    GPB_CK(cudaEventRecord(ex.ev_c[n_adv & 1], ms));
+    GPB_CK(cudaStreamWaitEvent(ex.inv, ex.ev_c[n_adv & 1], 0));
+    ++n_adv;
+    const long long fc = (long long)kc * GPB_NB;
+    return sched.advance<Cfg>(dm, fc >= n_max ? n_max : fc, ex.inv);
+  };
   auto full_with_rows = [&](int k) {   // block k (of the largest matrix) is a full pivot block with rows below it
     return k < nblk && (k + 1) * GPB_NB <= n_max && nrows - (k + 1) * GPB_NB > 0;
   };
@@ -653,7 +746,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   int step = 0;
   for (int k = 0; k < nblk;) {
     GPB_CK(diag(k));
-    if (!full_with_rows(k)) { ++k; continue; }
+    if (!full_with_rows(k)) { GPB_CK(inverse_progress(k + 1)); ++k; continue; }
     GPB_CK(panel(k));
     int kb = 1;
     bool waited = false;
@@ -665,6 +758,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
       GPB_CK(panel(k + 1));
       kb = 2;
     }
+    GPB_CK(inverse_progress(k + kb));
     const int rows = nrows - (k + kb) * GPB_NB;
     const int Tn = (rows + GPB_NB - 1) / GPB_NB;
     if (!lookahead) {
@@ -681,6 +775,12 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     k += kb;
     ++step;
   }
+  if (fuse) {
+    GPB_CK(inverse_progress(nblk));
+    if (!sched.finished()) return cudaErrorUnknown;      // the task graph must drain once every column is final
+    GPB_CK(cudaEventRecord(ex.ev_join[2], ex.inv));
+    GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[2], 0));
+  }
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
     GPB_CK(cudaEventRecord(ex.ev_join[1], ex.side));
@@ -690,9 +790,9 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   return cudaSuccess;
 }
 
-cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, const Exec& ex) {
-  return cfg_half() ? potrf_impl<CfgHalf>(dm, B, n_max, aug, lookahead, ex)
-                    : potrf_impl<CfgBig>(dm, B, n_max, aug, lookahead, ex);
+cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahead, bool with_trtri, const Exec& ex) {
+  return cfg_half() ? potrf_impl<CfgHalf>(dm, B, n_max, aug, lookahead, with_trtri, ex)
+                    : potrf_impl<CfgBig>(dm, B, n_max, aug, lookahead, with_trtri, ex);
 }
 
 cudaError_t run_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
@@ -710,14 +810,14 @@ cudaError_t run_finalize(const GpbMat* dm, int B, double log2pi, cudaStream_t s)
 template <class Cfg>
 static cudaError_t trtri_impl(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
-  diag_copy_kernel<<<dim3(nblk, B), 256, 0, s>>>(dm);
+  diag_copy_kernel<<<dim3(nblk, B), 256, 0, s>>>(dm, 0);
   ++g_launches;
   GPB_CK(cudaGetLastError());
   for (long long sz = GPB_NB; sz < n_max; sz *= 2) {
     const int tiles = (int)(sz / Cfg::BM) * (int)(sz / Cfg::BN);
     const int nsub = (int)((n_max + 2 * sz - 1) / (2 * sz));
-    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriT{dm, (int)sz}, dim3(tiles, nsub, B), s)));
-    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriW{dm, (int)sz}, dim3(tiles, nsub, B), s)));
+    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriT{dm, (int)sz, 0}, dim3(tiles, nsub, B), s)));
+    GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriW{dm, (int)sz, 0}, dim3(tiles, nsub, B), s)));
   }
   return cudaSuccess;
 }
