@@ -657,7 +657,7 @@ struct TrtriSched {
       progress = false;
       const int newc = fc >= n ? nblk : (int)(fc / GPB_NB);
       if (newc > copied) {
-        diag_copy_kernel<<<dim3(newc - copied, 1), 256, 0, st>>>(dm, copied);
+        diag_copy_kernel<<<dim3(newc - copied, 1), 1024, 0, st>>>(dm, copied);
         ++g_launches;
         GPB_CK(cudaGetLastError());
         copied = newc; progress = true;
@@ -810,7 +810,7 @@ cudaError_t run_finalize(const GpbMat* dm, int B, double log2pi, cudaStream_t s)
 template <class Cfg>
 static cudaError_t trtri_impl(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
   const int nblk = (n_max + GPB_NB - 1) / GPB_NB;
-  diag_copy_kernel<<<dim3(nblk, B), 256, 0, s>>>(dm, 0);
+  diag_copy_kernel<<<dim3(nblk, B), 1024, 0, s>>>(dm, 0);
   ++g_launches;
   GPB_CK(cudaGetLastError());
   for (long long sz = GPB_NB; sz < n_max; sz *= 2) {
