@@ -44,6 +44,8 @@ SIGNATURES = {
     "gpb_plan_create_dist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
     "gpb_dist_owner": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "gpb_dist_panel_segments": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_int_p]),
+    "gpb_trtri_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, c_int_p,
+                                          ctypes.c_int]),
     "gpb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 

@@ -515,6 +515,13 @@ int gpb_dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_c
   return 0;
 }
 
+int gpb_trtri_schedule(int n, const long long* final_cols, int n_steps, int* tasks, int capacity) {
+  if (n < 1) return fail_arg(1, "n < 1");
+  if (!final_cols || n_steps < 1) return fail_arg(2, "no progress sequence");
+  if (!tasks && capacity > 0) return fail_arg(4, "tasks is null");
+  return gpb::trtri_schedule_host(n, final_cols, n_steps, tasks, capacity);
+}
+
 int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
              int M, int N, int K, double alpha, double beta, void* stream) {
   if (!A) return fail_arg(3, "A is null");

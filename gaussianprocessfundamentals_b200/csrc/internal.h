@@ -35,6 +35,7 @@ cudaError_t run_symmetrize(double* A, int n, int ld, cudaStream_t s);
 cudaError_t run_gemm_plain(int akm, int bkm, const double* A, int lda, const double* Bm, int ldb, double* C, int ldc,
                            int M, int N, int K, double alpha, double beta, cudaStream_t s);
 cudaError_t run_microbench(int kind, int iters, int blocks, cudaStream_t s);
+int trtri_schedule_host(int n, const long long* fc, int n_fc, int* out, int cap);   // host-only: the overlapped inverse's schedule
 int potrf_outer_blocks(int n_max);   // 128-blocks per outer panel of the factorisation (1 or 2; GPB_POTRF_KB)
 cudaError_t linalg_init();
 

@@ -650,28 +650,27 @@ struct TrtriSched {
     for (int li = 0; li < nlev; ++li) if (nextW[li] < nsub[li]) return false;
     return true;
   }
-  template <class Cfg>
-  cudaError_t advance(const GpbMat* dm, long long fc, cudaStream_t st) {
+  // Launches everything that became ready now that columns [0, fc) of L are final.  `L` issues the work:
+  //   L.copy(first block, count), L.T(level s, first sub-problem, count), L.W(level s, first sub-problem, count)
+  template <class Launcher>
+  cudaError_t advance(long long fc, Launcher& L) {
     bool progress = true;
     while (progress) {
       progress = false;
       const int newc = fc >= n ? nblk : (int)(fc / GPB_NB);
       if (newc > copied) {
-        diag_copy_kernel<<<dim3(newc - copied, 1), 1024, 0, st>>>(dm, copied);
-        ++g_launches;
-        GPB_CK(cudaGetLastError());
+        GPB_CK(L.copy(copied, newc - copied));
         copied = newc; progress = true;
       }
       for (int li = 0; li < nlev; ++li) {
         const long long s = (long long)GPB_NB << li;
-        const int tiles = (int)(s / Cfg::BM) * (int)(s / Cfg::BN);
         int cnt = 0;
         while (nextT[li] + cnt < nsub[li]) {
           const long long rA = 2 * s * (nextT[li] + cnt) + s;
           if (rA <= fc && lower_done(li, rA)) ++cnt; else break;
         }
         if (cnt) {
-          GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriT{dm, (int)s, nextT[li]}, dim3(tiles, cnt, 1), st)));
+          GPB_CK(L.T((int)s, nextT[li], cnt));
           nextT[li] += cnt; progress = true;
         }
         cnt = 0;
@@ -680,7 +679,7 @@ struct TrtriSched {
           if ((end < n ? end : n) <= fc && lower_done(li, end)) ++cnt; else break;
         }
         if (cnt) {
-          GPB_CK((launch_cfg<Cfg, false, true>(GeoTrtriW{dm, (int)s, nextW[li]}, dim3(tiles, cnt, 1), st)));
+          GPB_CK(L.W((int)s, nextW[li], cnt));
           nextW[li] += cnt; progress = true;
         }
       }
@@ -688,6 +687,51 @@ struct TrtriSched {
     return cudaSuccess;
   }
 };
+
+template <class Cfg>
+struct TrtriDeviceLauncher {        // the scheduler's tasks as kernel launches on one stream
+  const GpbMat* dm;
+  cudaStream_t st;
+  cudaError_t copy(int k0, int cnt) {
+    diag_copy_kernel<<<dim3(cnt, 1), 1024, 0, st>>>(dm, k0);
+    ++g_launches;
+    return cudaGetLastError();
+  }
+  cudaError_t T(int s, int p0, int cnt) {
+    const int tiles = (s / Cfg::BM) * (s / Cfg::BN);
+    return launch_cfg<Cfg, false, true>(GeoTrtriT{dm, s, p0}, dim3(tiles, cnt, 1), st);
+  }
+  cudaError_t W(int s, int p0, int cnt) {
+    const int tiles = (s / Cfg::BM) * (s / Cfg::BN);
+    return launch_cfg<Cfg, false, true>(GeoTrtriW{dm, s, p0}, dim3(tiles, cnt, 1), st);
+  }
+};
+
+struct TrtriRecorder {              // host-only: records the schedule (tests)
+  int* out; int cap, count; long long fc;
+  cudaError_t put(int kind, int s, int p0, int cnt) {
+    for (int q = 0; q < cnt; ++q) {
+      if (count < cap) { out[4 * count] = kind; out[4 * count + 1] = s; out[4 * count + 2] = p0 + q; out[4 * count + 3] = (int)fc; }
+      ++count;
+    }
+    return cudaSuccess;
+  }
+  cudaError_t copy(int k0, int cnt) { return put(0, GPB_NB, k0, cnt); }
+  cudaError_t T(int s, int p0, int cnt) { return put(1, s, p0, cnt); }
+  cudaError_t W(int s, int p0, int cnt) { return put(2, s, p0, cnt); }
+};
+
+int trtri_schedule_host(int n, const long long* fc, int n_fc, int* out, int cap) {
+  TrtriSched sched;
+  sched.init(n);
+  TrtriRecorder rec{out, cap, 0, 0};
+  for (int i = 0; i < n_fc; ++i) {
+    rec.fc = fc[i];
+    sched.advance(fc[i] >= n ? (long long)n : fc[i], rec);
+  }
+  return sched.finished() ? rec.count : -rec.count - 1;
+}
+
 
 
 template <class Cfg>
@@ -713,7 +757,8 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     GPB_CK(cudaStreamWaitEvent(ex.inv, ex.ev_c[n_adv & 1], 0));
     ++n_adv;
     const long long fc = (long long)kc * GPB_NB;
-    return sched.advance<Cfg>(dm, fc >= n_max ? n_max : fc, ex.inv);
+    TrtriDeviceLauncher<Cfg> launcher{dm, ex.inv};
+    return sched.advance(fc >= n_max ? (long long)n_max : fc, launcher);
   };
   auto full_with_rows = [&](int k) {   // block k (of the largest matrix) is a full pivot block with rows below it
     return k < nblk && (k + 1) * GPB_NB <= n_max && nrows - (k + 1) * GPB_NB > 0;

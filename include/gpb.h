@@ -142,6 +142,13 @@ int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double*
 int gpb_zero_upper(double* A, int n, int ld, void* stream);   /* zero the strict upper triangle (column-major) */
 int gpb_symmetrize(double* A, int n, int ld, void* stream);   /* copy the lower triangle into the upper one    */
 
+/* Host arithmetic (no GPU): the schedule of the triangular inverse that gpb_plan_eval overlaps with the factorisation
+ * of one large matrix.  final_cols[i] = number of columns of L that are final at progress point i (non-decreasing, the
+ * last one >= n).  tasks receives 4 ints per task in launch order: kind (0 copy of an inverted diagonal block, 1 phase
+ * T = L21 W11, 2 phase W21 = -W22 T), level size s, index (block / sub-problem), final_cols at launch.  Returns the
+ * number of tasks (also when it exceeds capacity), or a negative value if the task graph did not drain.              */
+int gpb_trtri_schedule(int n, const long long* final_cols, int n_steps, int* tasks, int capacity);
+
 /* FP64 pipe probe used by bench.py to measure the roofline denominator: kind 0 = DMMA.8x8x4 (512 flop per warp
  * instruction), kind 1 = DFMA (64 flop per warp instruction); every thread issues 8 (kind 0) / 16 (kind 1)
  * independent instructions per iteration; `blocks` CTAs of 256 threads.                                         */

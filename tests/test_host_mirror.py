@@ -243,3 +243,78 @@ def test_lbfgs_fitter_host_logic_without_device(monkeypatch):
     target[0] = torch.tensor(2.0, dtype=torch.float64)           # optimum outside the box: the fit stops at the bound
     pre, post, hps, noise, _ = f.fit()
     assert abs(float(torch.as_tensor(hps[0])) - 1.0 / 3.0) < 1e-9
+
+
+def test_overlapped_inverse_task_graph_respects_its_dependencies():
+    """gpb_trtri_schedule (include/gpb.h) runs the scheduler that gpb_plan_eval uses to overlap the recursive-doubling
+    inverse with the factorisation - host arithmetic only.  For several sizes and progress sequences: every task is
+    launched exactly once, never before the columns of L it reads are final, T before W of a sub-problem, and the inverses
+    of the two diagonal halves (all lower-level tasks and block copies inside them) before the task that multiplies
+    with them."""
+    import ctypes
+    import random
+    lib = _lib.load()
+    NB = 128
+
+    def schedule(n, fcs):
+        arr = (ctypes.c_longlong * len(fcs))(*fcs)
+        cap = 4 * (n // NB + 2) * 4
+        out = (ctypes.c_int * (4 * cap))()
+        cnt = lib.gpb_trtri_schedule(n, arr, len(fcs), out, cap)
+        assert 0 <= cnt <= cap, (n, cnt)
+        return [tuple(out[4 * i:4 * i + 4]) for i in range(cnt)]
+
+    def check(n, fcs):
+        tasks = schedule(n, fcs)
+        pos = {}
+        for i, (kind, s, p, fc) in enumerate(tasks):
+            assert (kind, s, p) not in pos
+            pos[(kind, s, p)] = i
+        nblk = (n + NB - 1) // NB
+        levels = []
+        s = NB
+        while s < n:
+            levels.append((s, (n - s + 2 * s - 1) // (2 * s)))
+            s *= 2
+        assert all((0, NB, j) in pos for j in range(nblk))
+        assert all((1, s, p) in pos and (2, s, p) in pos for s, cnt in levels for p in range(cnt))
+        assert len(tasks) == nblk + 2 * sum(cnt for _, cnt in levels)
+
+        def inverse_complete_before(lo, hi, i):
+            hi = min(hi, n)
+            if any(pos[(0, NB, j)] >= i for j in range(lo // NB, (hi + NB - 1) // NB)):
+                return False
+            for s, cnt in levels:
+                for p in range(cnt):
+                    r0, rA = 2 * s * p, 2 * s * p + s
+                    if r0 >= lo and rA < hi and pos[(2, s, p)] >= i:
+                        return False
+            return True
+
+        for (kind, s, p), i in pos.items():
+            fc = tasks[i][3]
+            if kind == 0:
+                assert min((p + 1) * NB, n) <= fc
+            else:
+                r0, rA = 2 * s * p, 2 * s * p + s
+                if kind == 1:
+                    assert rA <= fc and inverse_complete_before(r0, rA, i)
+                else:
+                    assert min(rA + s, n) <= fc and pos[(1, s, p)] < i and inverse_complete_before(rA, rA + s, i)
+
+    rng = random.Random(3)
+    for n in (129, 255, 256, 257, 1000, 1024, 1025, 2321, 4096, 5000, 8192):
+        nblk = (n + NB - 1) // NB
+        two = []
+        k = 0
+        while k < nblk:                                   # the factorisation's progress with 256-wide outer panels
+            kb = 2 if k + 2 <= nblk - 1 else 1
+            two.append(min((k + kb) * NB, n))
+            k += kb
+        check(n, two + [n])
+        check(n, [min((k + 1) * NB, n) for k in range(nblk)] + [n])
+        check(n, sorted(rng.sample(range(0, n + 1), min(9, n))) + [n])
+        check(n, [n])
+    # a progress sequence that never reaches n leaves the graph undrained: reported as a negative count
+    arr = (ctypes.c_longlong * 1)(512)
+    assert lib.gpb_trtri_schedule(2048, arr, 1, None, 0) < 0
