@@ -340,3 +340,41 @@ def test_prediction_mse_bic_match_reference(gpb):
         assert np.max(np.abs(var - z[name + "/post_var"])) <= 1e-9 * max(1.0, np.max(np.abs(Ks))), name
         total, mean_mu, post = gp.predict(hp, None, noise)
         assert np.max(np.abs(total.cpu().numpy().reshape(-1) - z[name + "/predict_total"])) <= 1e-9 * scale, name
+
+
+def test_candidate_batch_matches_one_at_a_time(gpb):
+    """search.CandidateBatch (BASELINE config 3): all candidates in one batched plan = the reference's one metric per
+    candidate"""
+    g = gpb
+    from gaussianprocessfundamentals_b200 import search
+    rng = np.random.default_rng(33)
+    n = 257
+    x = np.sort(rng.uniform(0, 1, (n, 1)), axis=0)
+    y = np.sin(6 * x) + 0.5 * x + 0.1 * rng.standard_normal((n, 1))
+    specs = [["SE"], ["PER"], ["ADD", [["SE"], ["LIN"]]], ["MUL", [["SE"], ["PER"]]],
+             ["ADD", [["MUL", [["SE"], ["LIN"]]], ["PER"]]], ["MAT32"], ["MUL", [["MAT52"], ["LIN"]]]]
+    kernels = [build(g, s) for s in specs]
+    din = g.di.DataInput(x, y, x, y)
+    din.set_mean_function(g.bmf.ZeroMeanFunction(1))
+    hps = []
+    for k in kernels:
+        hp = []
+        for d in k.get_hyper_parameter_dimensionalities():
+            size = 1 if len(d) == 0 else d[0]
+            hp.append(torch.tensor(rng.uniform(0.3, 1.2, size=size)).reshape(d))
+        hps.append(hp)
+    noise = torch.tensor(1e-2, dtype=torch.float64)
+    batch = search.CandidateBatch(kernels, din)
+    nll, grads, gnoise = batch.evaluate(hps, noise)
+    for i, k in enumerate(kernels):
+        gp = g.gproc.GaussianProcess(k, g.bmf.ZeroMeanFunction(1))
+        gp.set_data_input(din)
+        metric = g.met_aux.get_metric_by_type(g.met.MetricType.LL, gp)
+        want = float(metric.get_metric(hps[i], noise, None))
+        wg, wn = metric.get_gradients(hps[i], noise, with_noise=True)
+        assert abs(nll[i] - want) <= LL_RTOL * abs(want), i
+        a = np.concatenate([np.asarray(t).reshape(-1) for t in grads[i]])
+        b = np.concatenate([np.asarray(t).reshape(-1) for t in wg])
+        assert np.max(np.abs(a - b)) <= GRAD_RTOL * np.max(np.abs(b)), i
+        assert abs(gnoise[i] - float(wn)) <= GRAD_RTOL * abs(float(wn)), i
+    assert batch.best(hps, noise) == int(np.argmin(nll))

@@ -207,3 +207,84 @@ def test_bench_workloads_partition_their_gps_across_ranks():
                     assert np.array_equal(h[pos], h1[b])
                     assert np.array_equal(ys[pos], y1[b]) and np.array_equal(xs[pos], x1[b])
             assert sorted(seen) == list(range(B))
+
+
+# ---- batched kernel search (search.CandidateBatch) on two ranks ---------------------------------------------------------
+CANDIDATES = [("SE",), ("PER",), ("ADD", [("SE",), ("LIN",)]), ("MUL", [("SE",), ("PER",)]),
+              ("ADD", [("MUL", [("SE",), ("LIN",)]), ("PER",)]), ("LIN",), ("MUL", [("PER",), ("LIN",)])]
+
+
+def _candidate_problem():
+    from gaussianprocessfundamentals_b200.DataHandling import DataInput as di
+    from gaussianprocessfundamentals_b200.KernelBasics import BaseKernels as bk, Operators as op
+    from gaussianprocessfundamentals_b200.MeanFunctionBasics import BaseMeanFunctions as bmf
+
+    def build(spec):
+        if spec[0] == "SE":
+            return bk.SquaredExponentialKernel(1)
+        if spec[0] == "PER":
+            return bk.PeriodicKernel(1)
+        if spec[0] == "LIN":
+            return bk.LinearKernel(1)
+        cls = op.AdditionOperator if spec[0] == "ADD" else op.MultiplicationOperator
+        return cls(1, [build(c) for c in spec[1]])
+
+    rng = np.random.default_rng(21)
+    n = 70
+    x = np.sort(rng.uniform(0, 1, (n, 1)), axis=0)
+    y = np.sin(6 * x) + 0.5 * x + 0.1 * rng.standard_normal((n, 1))
+    din = di.DataInput(x, y, x, y)
+    din.set_mean_function(bmf.ZeroMeanFunction(1))
+    kernels = [build(s) for s in CANDIDATES]
+    hps = []
+    for k in kernels:
+        hp = []
+        for d in k.get_hyper_parameter_dimensionalities():
+            size = 1 if len(d) == 0 else d[0]
+            hp.append(torch.tensor(rng.uniform(0.3, 1.2, size=size)).reshape(d))
+        hps.append(hp)
+    return kernels, din, hps
+
+
+def _candidate_eval():
+    from gaussianprocessfundamentals_b200 import search
+    kernels, din, hps = _candidate_problem()
+    batch = search.CandidateBatch(kernels, din)
+    batch._make_blocks = lambda ks, xs, ys: OracleBlocks(ks, xs, ys)
+    OracleBlocks.built_for = []
+    nll, grads, gnoise = batch.evaluate(hps, torch.tensor(1e-2, dtype=torch.float64))
+    flat = [np.concatenate([np.asarray(t).reshape(-1) for t in g]) for g in grads]
+    return nll, flat, gnoise, batch.sharding.mine, batch.best(hps, 1e-2)
+
+
+def _candidate_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out.put((rank,) + _candidate_eval())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_candidate_batch_two_ranks_gloo():
+    nll1, flat1, gn1, mine1, best1 = _candidate_eval()
+    assert mine1 == list(range(len(CANDIDATES)))
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_candidate_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([out.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shares = [g[4] for g in got]
+    assert sorted(shares[0] + shares[1]) == list(range(len(CANDIDATES))) and shares[0] and shares[1]
+    for rank, nll, flat, gn, mine, best in got:
+        assert np.array_equal(nll, nll1) and best == best1          # same oracle arithmetic per candidate
+        assert all(np.array_equal(a, b) for a, b in zip(flat, flat1))
+        assert np.array_equal(gn, gn1)
