@@ -161,3 +161,30 @@ def test_closed_form_white_noise():
     want = 0.5 * float((y.T @ y)[0, 0]) / 1.5 + 0.5 * n * math.log(1.5) + 0.5 * n * math.log(2 * math.pi)
     assert abs(val - want) <= 1e-13 * abs(want)
     assert abs(gn - (0.5 * n / 1.5 - 0.5 * float((y.T @ y)[0, 0]) / 1.5 ** 2)) <= 1e-12
+
+
+def test_reference_outputs_against_lapack_independent_of_torch(gold):
+    """The golden vectors were produced by the reference's own code on a TensorFlow stand-in whose leaf ops are torch's.
+    Guard against a shared torch artefact: recompute NLL, L and alpha of the stored cases with NumPy / SciPy LAPACK only
+    (no torch, no autodiff), from the kernel matrix K the reference itself produced."""
+    import scipy.linalg as sla
+    z, meta = gold
+    checked = 0
+    for name, m in meta.items():
+        if not (isinstance(m, dict) and m.get("kind") == "holistic" and (name + "/K") in z.files):
+            continue
+        K, y, s2 = z[name + "/K"], z[name + "/y"], float(z[name + "/noise"])
+        n = K.shape[0]
+        c, low = sla.cho_factor(K + s2 * np.eye(n), lower=True)
+        L = np.tril(c)
+        alpha = sla.cho_solve((c, low), y)
+        nll = 0.5 * float(y.T @ alpha) + float(np.sum(np.log(np.diag(L)))) + 0.5 * n * np.log(2 * np.pi)
+        assert abs(nll - float(z[name + "/nll"][0])) <= 1e-12 * abs(nll), name
+        assert np.max(np.abs(L - z[name + "/L"])) <= 1e-12 * np.max(np.abs(L)), name
+        assert np.max(np.abs(alpha - z[name + "/alpha"])) <= 1e-9 * np.max(np.abs(alpha)), name
+        # and the kernel matrix itself from the formulas of SURVEY App. A, in plain NumPy, for the SE case
+        if json.loads(m["spec"]) == ["SE"]:
+            x, l = z[name + "/x"], float(z[name + "/hp0"])
+            assert np.max(np.abs(K - np.exp(-0.5 * (x - x.T) ** 2 / (l * l)))) <= 1e-14, name
+        checked += 1
+    assert checked >= 2
