@@ -56,9 +56,22 @@ class Metric(AbstractMetric):
             self.last_covariance_matrix = self.covariance_matrix.get_K_noised(hyper_parameter, noise)
         return self.last_covariance_matrix
 
-    def get_alpha(self, hyper_parameter, noise, y=None, indices=None):
+    # The reference binds get_alpha / get_log_determinant to one of several handlers in its constructor
+    # (Metrics.py:77-107); with CHOLESKY_BASED - the only handler of the B200 path - these are the two below.
+    def get_alpha_cholesky(self, hyper_parameter, noise, y=None, indices=None):
+        """alpha = L^T \\ (L \\ y) (Metrics.py:138-139): blocked Cholesky with carried y + blocked back substitution"""
         return self.covariance_matrix.get_L_alpha(hyper_parameter, noise)
 
-    def get_log_determinant(self, hyper_parameter, noise, indices=None):
+    def get_log_determinant_cholesky(self, hyper_parameter, noise, indices=None):
+        """log det (K + s2 I) = 2 sum log diag L (Metrics.py:152-154)"""
         L = self.covariance_matrix.get_L_K(hyper_parameter, noise)
         return 2 * torch.sum(torch.log(torch.diagonal(L)))
+
+    def get_default_covariance_matrix(self, hyper_parameter, noise, indices=None):
+        return self.get_covariance_matrix(hyper_parameter, noise, indices)
+
+    def get_alpha(self, hyper_parameter, noise, y=None, indices=None):
+        return self.get_alpha_cholesky(hyper_parameter, noise, y, indices)
+
+    def get_log_determinant(self, hyper_parameter, noise, indices=None):
+        return self.get_log_determinant_cholesky(hyper_parameter, noise, indices)
