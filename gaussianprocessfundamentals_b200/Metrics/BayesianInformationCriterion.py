@@ -23,6 +23,21 @@ class BIC(AbstractBIC):
         penalty = self.covariance_matrix.kernel.get_number_of_hyper_parameter() * math.log(self.data_input.n_train)
         return 2 * nll + penalty
 
+    def _eval(self, hyper_parameter, noise, want_grad):
+        """(BIC, [d BIC / d hp], d BIC / d noise): the penalty is constant, so the gradient is twice the likelihood's
+        (what the reference's GradientTape yields when a fitter is built with MetricType.BIC, Optimizer/Fitter.py:154-158)"""
+        value, grads, gnoise = self.log_likelihood._eval(hyper_parameter, noise, want_grad)
+        penalty = self.covariance_matrix.kernel.get_number_of_hyper_parameter() * math.log(self.data_input.n_train)
+        if not want_grad:
+            return 2 * value + penalty, None, None
+        return 2 * value + penalty, [2 * torch.as_tensor(g, dtype=torch.float64) for g in grads], 2 * gnoise
+
+    def get_gradients(self, hyper_parameter, noise, reset: bool = True, with_noise: bool = False):
+        if reset:
+            self.covariance_matrix.reset()
+        _, grads, gnoise = self._eval(hyper_parameter, noise, True)
+        return (grads, torch.tensor(gnoise, dtype=torch.float64)) if with_noise else grads
+
 
 class BlockwiseBIC(AbstractMetric):
     def __init__(self, _gp, local_approx, numerical_matrix_handling, subset_size: int = None):
@@ -36,3 +51,15 @@ class BlockwiseBIC(AbstractMetric):
         nll = ll.get_metric(hyper_parameter, noise, indices)
         penalty = self._gp.covariance_matrix.kernel.get_number_of_hyper_parameter() * math.log(self._gp.data_input.n_train)
         return 2 * nll + penalty
+
+    def _eval(self, hyper_parameter, noise, want_grad):
+        ll = BlockwiseLogLikelihood(self._gp, self.local_approx, self.numerical_matrix_handling, self.subset_size)
+        value, grads, gnoise = ll._eval(hyper_parameter, noise, want_grad)
+        penalty = self._gp.covariance_matrix.kernel.get_number_of_hyper_parameter() * math.log(self._gp.data_input.n_train)
+        if not want_grad:
+            return 2 * value + penalty, None, None
+        return 2 * value + penalty, [2 * torch.as_tensor(g, dtype=torch.float64) for g in grads], 2 * gnoise
+
+    def get_gradients(self, hyper_parameter, noise, reset: bool = True, with_noise: bool = False):
+        _, grads, gnoise = self._eval(hyper_parameter, noise, True)
+        return (grads, torch.tensor(gnoise, dtype=torch.float64)) if with_noise else grads

@@ -64,6 +64,7 @@ class LogLikelihood(AbstractLogLikelihood):
                          subset_size)
         self.reference_batch_aggregate = reference_batch_aggregate
         self._batch_blocks = None
+        self._batch_weights = None
 
     # ---- evaluation ------------------------------------------------------------------------------------------------
     def _eval(self, hyper_parameter, noise, want_grad):
@@ -74,34 +75,41 @@ class LogLikelihood(AbstractLogLikelihood):
     def _eval_batch(self, hyper_parameter, noise, want_grad):
         """rank-3 input [B, n, d]: B GPs sharing kernel and hyper-parameters, one batched plan.  The reference sums
         the log-determinant over the whole batch before averaging (Metrics.py:153-154, LogLikelihood.py:49,62-63;
-        SURVEY App. B-3); `reference_batch_aggregate` reproduces that, otherwise the mean of the true per-entry NLLs is
-        returned."""
+        SURVEY App. B-3):   value = mean_b(1/2 y_b^T alpha_b) + sum_b sum(log diag L_b) + 1/2 n log(2 pi).
+        `reference_batch_aggregate` reproduces that (value and gradient: the aggregate is linear in the per-GP terms, so
+        the device reports every GP's gradient with the weights (1/B, 1) on its two terms and the host adds them up);
+        otherwise the mean of the true per-entry NLLs is returned."""
         from ..Statistics._device import DeviceBlocks
-        from .. import engine
         x, y = self.data_input.data_x_train, self.data_input.get_detrended_y_train()
         B, n = x.shape[0], x.shape[1]
         kern = self.covariance_matrix.kernel
+        if self._batch_blocks is not None and not self._batch_blocks.matches([kern] * B, y):
+            self._batch_blocks = None
         if self._batch_blocks is None:
-            self._batch_blocks = DeviceBlocks([kern] * B, [x[b] for b in range(B)], [y[b] for b in range(B)], True)
+            self._batch_blocks = DeviceBlocks([kern] * B, [x[b] for b in range(B)], [y[b] for b in range(B)], True,
+                                              y_source=y)
+            self._batch_weights = None
         blocks = self._batch_blocks
+        weights = (1.0 / B, 1.0) if self.reference_batch_aggregate else (1.0, 1.0)
+        if self._batch_weights != weights:
+            for b in range(B):
+                blocks.plan.set_grad_weights(b, *weights)
+            self._batch_weights = weights
         s2 = float(torch.as_tensor(noise, dtype=torch.float64))
         nll, grads = blocks.evaluate([hyper_parameter] * B, [s2] * B, want_grad)
+        kern._remember(hyper_parameter)
         const = 0.5 * n * np.log(np.pi * 2)
         if self.reference_batch_aggregate:
-            quad = np.array([-float(blocks.plan.buffer(b, engine.BUF_A)[n, n]) for b in range(B)]) if not want_grad \
-                else None
-            if quad is None:
-                raise NotImplementedError("gradient of the reference's batch aggregate is not defined on this path; "
-                                          "use reference_batch_aggregate=False")
-            half_logdet = nll - 0.5 * quad - const
+            quad, half_logdet = blocks.plan.last_terms()          # one D2H for the whole batch (part of eval_host)
             value = float(np.mean(0.5 * quad) + np.sum(half_logdet) + const)
-            return value, None, None
-        value = float(np.mean(nll))
+        else:
+            value = float(np.mean(nll))
         if not want_grad:
             return value, None, None
         glists, gnoise = blocks.grads_as_lists(grads, [hyper_parameter] * B)
-        mean_g = [sum(torch.as_tensor(g[i]) for g in glists) / B for i in range(len(hyper_parameter))]
-        return value, mean_g, float(np.mean(gnoise))
+        scale = 1.0 if self.reference_batch_aggregate else 1.0 / B
+        total = [sum(torch.as_tensor(g[i]) for g in glists) * scale for i in range(len(hyper_parameter))]
+        return value, total, float(np.sum(gnoise) * scale)
 
     def get_metric(self, hyper_parameter: List[torch.Tensor], noise, indices=None, reset: bool = True) -> torch.Tensor:
         if reset:

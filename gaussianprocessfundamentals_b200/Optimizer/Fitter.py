@@ -27,6 +27,11 @@ class Fitter:
     def __init__(self, data_input, gaussian_process, metric_type: met.MetricType, fitter_type: ft.FitterType,
                  from_distribution: bool, local_approx, numerical_matrix_handling, subset_size: int = None):
         self._gp = gaussian_process
+        if metric_type in (met.MetricType.MSE, met.MetricType.blockwise_MSE):
+            # the fitters drive the fused likelihood gradient of the device path; the adjoint of the posterior mean is
+            # not part of it (the reference would differentiate MSE through its GradientTape)
+            raise NotImplementedError("fitting on %s is not implemented on the B200 path: use MetricType.LL / BIC or "
+                                      "their blockwise variants" % metric_type)
         if isinstance(data_input, list):
             self.metric = []
             for instance in data_input:

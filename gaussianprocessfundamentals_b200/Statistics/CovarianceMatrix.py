@@ -77,13 +77,12 @@ class HolisticCovarianceMatrix(CovarianceMatrix):
     # ---- the fused path -------------------------------------------------------------------------------------------
     def _device_blocks(self) -> DeviceBlocks:
         self._need_data()
-        scaled, cp = bool(global_param.p_scaled_base_kernel), global_param.cp_mode_code()
-        if self._blocks is not None:
-            prog = engine.DeviceProgram.get(self.kernel.to_spec(), self.kernel.get_dimensionality(), scaled, cp)
-            if self._blocks.key[0] != (prog.compiled.signature(),) or self._blocks.key[2:4] != (scaled, cp):
-                self._blocks = None
+        # the reference re-reads get_detrended_y_train() on every get_metric: a new mean function or edited targets must
+        # reach the device too, so the plan is keyed on the kernel program AND on the target tensor's identity / version
+        y = self.data_input.get_detrended_y_train()
+        if self._blocks is not None and not self._blocks.matches([self.kernel], y):
+            self._blocks = None
         if self._blocks is None:
-            y = self.data_input.get_detrended_y_train()
             self._blocks = DeviceBlocks([self.kernel], [self.data_input.data_x_train], [y], want_grad=True,
                                         grid=getattr(self, "_grid", None))
         return self._blocks
@@ -249,12 +248,14 @@ class SegmentedCovarianceMatrix(CovarianceMatrix):
 
     def _device_blocks(self) -> DeviceBlocks:
         self._need_data()
+        act = self._active()
+        act = [act[p] for p in self._local_positions(act)]
+        kernels = [self.kernel.child_nodes[i] for i in act]
+        ys = [self.data_input.data_inputs[i].get_detrended_y_train() for i in act]
+        if self._blocks is not None and not self._blocks.matches(kernels, ys):
+            self._blocks = None       # a child kernel, a global switch or the detrended targets changed
         if self._blocks is None:
-            act = self._active()
-            act = [act[p] for p in self._local_positions(act)]
-            kernels = [self.kernel.child_nodes[i] for i in act]
             xs = [self.data_input.data_inputs[i].data_x_train for i in act]
-            ys = [self.data_input.data_inputs[i].get_detrended_y_train() for i in act]
             self._blocks = self._make_blocks(kernels, xs, ys) if act else None
         return self._blocks
 
@@ -346,6 +347,9 @@ class SegmentedCovarianceMatrix(CovarianceMatrix):
         return out
 
     def _factor_blocks(self, hyper_parameter, noise, inverse: bool):
+        if getattr(self, "_sharding", None) is not None:
+            raise RuntimeError("the per-block matrix getters are single-process: this covariance matrix was shard()ed "
+                               "and holds only this rank's blocks (use block_nll_and_grad, or an unsharded copy)")
         blocks = self._device_blocks()
         act, sl = self._active(), self._slices()
         blocks.evaluate([list(hyper_parameter[sl[i]]) for i in act], [_noise_value(noise)] * len(act), inverse)

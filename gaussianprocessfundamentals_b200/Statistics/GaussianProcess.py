@@ -55,9 +55,14 @@ class AbstractGaussianProcess:
             mus = []
             for sub_gp in self.constituent_gps:
                 c = sub_gp.kernel.get_number_of_hyper_parameter()
-                if sub_gp.data_input.n_train > 0 and sub_gp.data_input.n_test > 0:
+                n_test = int(sub_gp.data_input.n_test)
+                if sub_gp.data_input.n_train > 0 and n_test > 0:
                     sub_gp.aux.reset(); sub_gp.covariance_matrix.reset()
                     mus.append(sub_gp.aux.get_posterior_mu(list(kernel_hyper_param[index:index + c]), noise))
+                elif n_test > 0:
+                    # test points in a block without training points: the posterior is the prior, whose mean is 0 (the
+                    # reference cannot build such a block at all); keeps the concatenation aligned with data_x_test
+                    mus.append(torch.zeros(n_test, dtype=torch.float64, device="cuda"))
                 index += c
             posterior_mu = torch.cat(mus, dim=0)
         else:

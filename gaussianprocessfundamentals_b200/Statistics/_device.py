@@ -14,7 +14,9 @@ class DeviceBlocks:
     """B independent (kernel, X, y) blocks evaluated as one batched plan."""
 
     def __init__(self, kernels: Sequence, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor], want_grad: bool = True,
-                 grid=None):
+                 grid=None, y_source=None):
+        """y_source: the tensor(s) the detrended targets were taken from (default: `ys`); `matches` compares their
+        identity and in-place version so that a new mean function or edited targets are uploaded again."""
         engine.require_cuda()
         self.kernels = list(kernels)
         self.ns = [int(x.shape[0]) for x in xs]
@@ -29,6 +31,23 @@ class DeviceBlocks:
             self.plan.set_data(b, x, y)
         self.holds = None          # "L" after the factorisation, "W" after the inverse
         self.last = None           # (nll[B], grads[B], info[B]) of the latest evaluation
+        self._y_source = ys if y_source is None else y_source     # strong reference: ids are compared, never reused
+        self._y_stamp = self._stamp(self._y_source)
+
+    @staticmethod
+    def _stamp(ys):
+        ys = ys if isinstance(ys, (list, tuple)) else [ys]
+        return tuple((id(t), getattr(t, "_version", 0)) for t in ys)
+
+    def matches(self, kernels: Sequence, y_source) -> bool:
+        """same kernel programs, same global switches and the same (unmodified) target tensors as at construction"""
+        scaled = bool(global_param.p_scaled_base_kernel)
+        cp_mode = global_param.cp_mode_code()
+        if len(kernels) != len(self.programs) or (scaled, cp_mode) != self.key[2:4]:
+            return False
+        from ..program import compile_spec
+        sigs = tuple(compile_spec(k.to_spec(), k.get_dimensionality(), scaled).signature() for k in kernels)
+        return sigs == self.key[0] and self._stamp(y_source) == self._y_stamp
 
     def flat_hp(self, hp_lists: Sequence[list]) -> List[np.ndarray]:
         return [flatten_hp(p.compiled.entries, hp, p.n_hp) for p, hp in zip(self.programs, hp_lists)]

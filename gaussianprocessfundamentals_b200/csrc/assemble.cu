@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   int ti, tj;
   if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
   const int P = d.n_hp + 1;
+  if (*d.info != 0) return;     // failed factorisation: grad_reduce_kernel writes NaN, nothing to sum
   if (d.col_world && (tj / (GPB_NB / A_T)) % d.col_world != d.col_rank) {
     // distributed plan: another rank owns this block column; its partial sums are zero here
     for (int pp = threadIdx.x; pp < P; pp += 256) d.gpart[(size_t)blockIdx.x * P + pp] = 0.0;
@@ -168,13 +169,14 @@ __global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ ma
   p.xi = s_xi + r * d.dim; p.dim = d.dim; p.hp = s_hp; p.ihp = s_ihp; p.cp_mode = d.cp_mode; p.gi = gi;
   if (gi < d.n) {
     const double ai = s_ai[r];
+    const double gwl = d.gw_logdet, gwq = d.gw_quad;
 #pragma unroll 1
     for (int q = 0; q < A_T / 4; ++q) {
       const int c = cg + 4 * q;
       const int gj = j0 + c;
       if (gj >= d.n || gj > gi) continue;
       const double kinv = d.Kinv[gi + (size_t)gj * d.ld];
-      double w = 0.5 * (kinv - ai * s_aj[c]);
+      double w = 0.5 * (gwl * kinv - gwq * (ai * s_aj[c]));
       if (gi == gj) acc(d.n_hp, w); else w *= 2.0;
       p.xj = s_xj + c * d.dim; p.gj = gj;
       gpb_eval_grad(s_code, d.n_ops, p, w, acc);

@@ -41,7 +41,8 @@ struct gpb_program {
   int32_t* code_dev;
 };
 
-enum { NBUF = 11 };
+enum { NBUF = 12 };
+enum { HOLDS_NONE = 0, HOLDS_K = 1, HOLDS_L = 2, HOLDS_W = 3 };
 struct PlanMat {
   int64_t n;
   int ld, nblk, n_hp, n_gtiles;
@@ -54,7 +55,11 @@ struct gpb_plan {
   std::vector<PlanMat> mats;
   std::vector<const gpb_program*> progs;
   size_t ws_bytes, off_desc, off_in, in_bytes, off_out, out_bytes;
-  size_t off_hp_all, off_noise_all, off_nll_all, off_grad_all, off_info_all;
+  size_t off_hp_all, off_noise_all, off_nll_all, off_grad_all, off_info_all, off_terms_all;
+  size_t off_data, data_bytes;   // X and y of all GPs, contiguous: one H2D when the caller's buffers share the layout
+  int holds;                     // what GPB_BUF_A currently holds (HOLDS_*): stages are checked against it
+  int have_kinv;                 // GPB_BUF_KINV holds inv(K) of the current factorisation
+  std::vector<double> gw;        // [2 B] gradient weights (quad, logdet) per GP
   std::vector<size_t> hp_prefix, grad_prefix;
   char* ws;
   int n_max, n_hp_max, n_ops_max, dim;
@@ -71,11 +76,40 @@ struct gpb_plan {
   gpb::DistCtx* dist;       // non-null: ONE GP factorised over a process grid (dist.cu)
   size_t off_stage[2];      // panel staging buffers of a distributed plan
   GpbMat h_desc0;           // host copy of the first descriptor (distributed plans)
+  std::vector<GpbMat> h_desc;   // host copy of all descriptors
 };
 
 struct gpb_dist {
   gpb::DistCtx* ctx;
 };
+
+// What the factorisation buffer holds decides which stages may run (a stage on the wrong content would read garbage
+// silently): K -> POTRF -> L -> {NLL, BACKSOLVE, TRTRI} ; TRTRI -> W -> {LAUUM} ; LAUUM -> inv(K) -> {GRAD}.
+// The single-GPU inverse leaves the carried row z^T intact, so NLL alone stays legal after it; the distributed exchange
+// of W overwrites it.
+static int advance_state(gpb_plan* p, int stages) {
+  int holds = p->holds, kinv = p->have_kinv;
+  if (stages & GPB_STAGE_ASSEMBLE) { holds = HOLDS_K; kinv = 0; }
+  if (stages & GPB_STAGE_POTRF) {
+    if (holds != HOLDS_K) return fail_arg(2, "POTRF needs a freshly assembled matrix (run GPB_STAGE_ASSEMBLE first)");
+    holds = HOLDS_L;
+  }
+  if ((stages & GPB_STAGE_BACKSOLVE) && holds != HOLDS_L)
+    return fail_arg(2, "BACKSOLVE needs the Cholesky factor: the buffer holds its inverse (or nothing); re-run ASSEMBLE | POTRF");
+  if ((stages & GPB_STAGE_NLL) && holds != HOLDS_L && !(holds == HOLDS_W && !p->dist))
+    return fail_arg(2, "NLL needs the Cholesky factor (run ASSEMBLE | POTRF first)");
+  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
+    if (holds != HOLDS_L) return fail_arg(2, "TRTRI needs the Cholesky factor (run ASSEMBLE | POTRF first)");
+    holds = HOLDS_W;
+  }
+  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) {
+    if (holds != HOLDS_W) return fail_arg(2, "LAUUM needs W = inv(L) (run TRTRI first)");
+    kinv = 1;
+  }
+  if ((stages & GPB_STAGE_GRAD) && !kinv) return fail_arg(2, "GRAD needs inv(K) (run INVERSE first)");
+  p->holds = holds; p->have_kinv = kinv;
+  return 0;
+}
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -192,7 +226,20 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   p->off_nll_all = off; off += (size_t)B * 8;
   p->off_grad_all = off; off += p->grad_prefix[B] * 8;
   p->off_info_all = off; off += (size_t)B * 4;
+  off = (off + 7) & ~(size_t)7;
+  p->off_terms_all = off; off += (size_t)B * 16;
   p->out_bytes = off - p->off_out; off = al(off);
+  p->holds = HOLDS_NONE; p->have_kinv = 0;
+  p->gw.assign((size_t)2 * B, 1.0);
+  // the inputs of all GPs form one contiguous region (X_0 | y_0 | X_1 | y_1 | ...)
+  p->off_data = off;
+  for (int b = 0; b < B; ++b) {
+    PlanMat& m = p->mats[b];
+    auto put = [&](int which, size_t bytes) { m.off[which] = off; m.bytes[which] = bytes; off = al(off + bytes); };
+    put(GPB_BUF_X, (size_t)n[b] * progs[b]->dim * 8);
+    put(GPB_BUF_Y, (size_t)n[b] * 8);
+  }
+  p->data_bytes = off - p->off_data;
   for (int b = 0; b < B; ++b) {
     PlanMat& m = p->mats[b];
     const gpb_program* g = progs[b];
@@ -202,8 +249,6 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     m.n_hp = g->n_hp;
     m.n_gtiles = gpb::grad_tiles((int)n[b]);
     auto put = [&](int which, size_t bytes) { m.off[which] = off; m.bytes[which] = bytes; off = al(off + bytes); };
-    put(GPB_BUF_X, (size_t)n[b] * g->dim * 8);
-    put(GPB_BUF_Y, (size_t)n[b] * 8);
     put(GPB_BUF_ALPHA, (size_t)n[b] * 8);
     put(GPB_BUF_Z, (size_t)n[b] * 8);
     m.off_tmpv = off; off = al(off + (size_t)n[b] * 8);
@@ -217,6 +262,7 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     m.off[GPB_BUF_NLL] = p->off_nll_all + (size_t)b * 8; m.bytes[GPB_BUF_NLL] = 8;
     m.off[GPB_BUF_GRAD] = p->off_grad_all + p->grad_prefix[b] * 8; m.bytes[GPB_BUF_GRAD] = (size_t)(g->n_hp + 1) * 8;
     m.off[GPB_BUF_INFO] = p->off_info_all + (size_t)b * 4; m.bytes[GPB_BUF_INFO] = 4;
+    m.off[GPB_BUF_TERMS] = p->off_terms_all + (size_t)b * 16; m.bytes[GPB_BUF_TERMS] = 16;
   }
   if (dist) {
     for (int i = 0; i < 2; ++i) { p->off_stage[i] = off; off = al(off + gpb::dist_stage_bytes((int)n[0])); }
@@ -295,6 +341,8 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     d.nll = (double*)(w + m.off[GPB_BUF_NLL]);
     d.grad = (double*)(w + m.off[GPB_BUF_GRAD]);
     d.info = (int*)(w + m.off[GPB_BUF_INFO]);
+    d.terms = (double*)(w + m.off[GPB_BUF_TERMS]);
+    d.gw_quad = p->gw[2 * b]; d.gw_logdet = p->gw[2 * b + 1];
     d.n = (int)m.n; d.ld = m.ld; d.dim = g->dim; d.n_ops = g->n_ops; d.n_hp = g->n_hp; d.aug = 1;
     d.cp_mode = g->cp_mode; d.n_gtiles = m.n_gtiles;
     if (p->dist) {
@@ -303,6 +351,8 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     }
   }
   p->h_desc0 = h[0];
+  p->h_desc = h;
+  p->holds = HOLDS_NONE; p->have_kinv = 0;
   CU(cudaMemcpy(p->ws + p->off_desc, h.data(), (size_t)p->B * sizeof(GpbMat), cudaMemcpyHostToDevice), "gpb_plan_bind");
   CU(cudaMemset(p->ws + p->off_out, 0, p->out_bytes), "gpb_plan_bind");
   return 0;
@@ -325,6 +375,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   if (!p->ws) return fail_arg(1, "plan is not bound");
   if ((stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI | GPB_STAGE_LAUUM | GPB_STAGE_GRAD)) && !p->want_grad)
     return fail_arg(2, "plan was created without gradient workspace");
+  { const int rc_state = advance_state(p, stages); if (rc_state) return rc_state; }
   cudaStream_t s = (cudaStream_t)stream;
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
   p->ex.main = s;
@@ -402,11 +453,24 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
   if (!hp_host && p->hp_prefix[p->B] > 0) return fail_arg(5, "hp_host is null");
   if (!noise_host) return fail_arg(6, "noise_host is null");
   cudaStream_t s = (cudaStream_t)stream;
+  // Fewer, larger copies: when the caller's X / y buffers are laid out like the plan's data region (one staging buffer,
+  // gpb_plan_input_layout) all inputs travel in ONE cudaMemcpyAsync instead of 2 B of them (1024 blocks: 2048 copies
+  // cost a sixth of the evaluation).
+  bool packed = X_host && y_host && p->B > 1;
+  if (packed) {
+    const char* base = (const char*)X_host[0] - (p->mats[0].off[GPB_BUF_X] - p->off_data);
+    for (int b = 0; b < p->B && packed; ++b) {
+      const PlanMat& m = p->mats[b];
+      packed = X_host[b] && y_host[b] && (const char*)X_host[b] == base + (m.off[GPB_BUF_X] - p->off_data) &&
+               (const char*)y_host[b] == base + (m.off[GPB_BUF_Y] - p->off_data);
+    }
+    if (packed) CU(cudaMemcpyAsync(p->ws + p->off_data, base, p->data_bytes, cudaMemcpyHostToDevice, s), "H2D X, y (packed)");
+  }
   for (int b = 0; b < p->B; ++b) {
     const PlanMat& m = p->mats[b];
-    if (X_host && X_host[b])
+    if (!packed && X_host && X_host[b])
       CU(cudaMemcpyAsync(p->ws + m.off[GPB_BUF_X], X_host[b], m.bytes[GPB_BUF_X], cudaMemcpyHostToDevice, s), "H2D X");
-    if (y_host && y_host[b])
+    if (!packed && y_host && y_host[b])
       CU(cudaMemcpyAsync(p->ws + m.off[GPB_BUF_Y], y_host[b], m.bytes[GPB_BUF_Y], cudaMemcpyHostToDevice, s), "H2D y");
     if (m.n_hp > 0) memcpy(p->h_in + (p->off_hp_all - p->off_in) + p->hp_prefix[b] * 8, hp_host[b], (size_t)m.n_hp * 8);
   }
@@ -417,9 +481,10 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
   // once per stage mask and replayed: the inputs live at fixed addresses inside the workspace.  Distributed plans launch
   // directly (their NCCL calls are ordered with the other ranks by the host loop).
   cudaGraphExec_t exec = nullptr;
+  bool exec_cached = false;
   if (!p->dist && !p->graphs_off) {
     for (int i = 0; i < p->n_graphs; ++i)
-      if (p->graph_stages[i] == stages) exec = p->graph_exec[i];
+      if (p->graph_stages[i] == stages) { exec = p->graph_exec[i]; exec_cached = true; }
     if (!exec && p->n_graphs < 4) {
       cudaGraph_t graph = nullptr;
       cudaError_t ce = cudaStreamBeginCapture(p->gstream, cudaStreamCaptureModeThreadLocal);
@@ -438,6 +503,10 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
     }
   }
   if (exec) {
+    if (exec_cached) {   // a replay repeats the transitions the capture call made
+      const int rc_state = advance_state(p, stages);
+      if (rc_state) return rc_state;
+    }
     CU(cudaEventRecord(p->g_in, s), "graph fork");
     CU(cudaStreamWaitEvent(p->gstream, p->g_in, 0), "graph fork");
     CU(cudaGraphLaunch(exec, p->gstream), "graph launch");
@@ -452,6 +521,39 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
   if (nll_host) memcpy(nll_host, p->h_out + (p->off_nll_all - p->off_out), (size_t)p->B * 8);
   if (grad_host) memcpy(grad_host, p->h_out + (p->off_grad_all - p->off_out), p->grad_prefix[p->B] * 8);
   if (info_host) memcpy(info_host, p->h_out + (p->off_info_all - p->off_out), (size_t)p->B * 4);
+  return 0;
+}
+
+int gpb_plan_set_grad_weights(gpb_plan_t* p, int b, double w_quad, double w_logdet) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (b < 0 || b >= p->B) return fail_arg(2, "b out of range");
+  p->gw[2 * b] = w_quad; p->gw[2 * b + 1] = w_logdet;
+  if (p->ws) {
+    p->h_desc[b].gw_quad = w_quad; p->h_desc[b].gw_logdet = w_logdet;
+    if (b == 0) p->h_desc0 = p->h_desc[0];
+    CU(cudaMemcpy(p->ws + p->off_desc + (size_t)b * sizeof(GpbMat), &p->h_desc[b], sizeof(GpbMat), cudaMemcpyHostToDevice),
+       "gpb_plan_set_grad_weights");
+  }
+  return 0;
+}
+
+int gpb_plan_last_terms(const gpb_plan_t* p, double* quad_host, double* logdet_host) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (!p->h_out) return fail_arg(1, "plan has no host mirror");
+  const double* t = (const double*)(p->h_out + (p->off_terms_all - p->off_out));
+  for (int b = 0; b < p->B; ++b) {
+    if (quad_host) quad_host[b] = t[2 * b];
+    if (logdet_host) logdet_host[b] = t[2 * b + 1];
+  }
+  return 0;
+}
+
+int gpb_plan_input_layout(const gpb_plan_t* p, int b, size_t* x_offset, size_t* y_offset, size_t* total_bytes) {
+  if (!p) return fail_arg(1, "plan is null");
+  if (b < 0 || b >= p->B) return fail_arg(2, "b out of range");
+  if (x_offset) *x_offset = p->mats[b].off[GPB_BUF_X] - p->off_data;
+  if (y_offset) *y_offset = p->mats[b].off[GPB_BUF_Y] - p->off_data;
+  if (total_bytes) *total_bytes = p->data_bytes;
   return 0;
 }
 

@@ -24,6 +24,10 @@ struct GpbMat {
   double* nll;       // device scalar out
   double* grad;      // [n_hp+1] out (last entry: d nll / d s2)
   int* info;         // device scalar out: 0 ok, j>0 first non-positive pivot (1-based)
+  double* terms;     // [2] out: y^T K^-1 y and sum(log diag L), the two data-dependent terms of the NLL
+  // weights of the two terms in the gradient: d/dtheta [gw_quad * 1/2 y^T K^-1 y + gw_logdet * sum(log diag L)]
+  // (1, 1 = the NLL; the rank-3 batch aggregate of Metrics/LogLikelihood.py:62-63 uses 1/B and 1)
+  double gw_quad, gw_logdet;
   int n, ld, dim, n_ops, n_hp, aug, cp_mode, n_gtiles;
   // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, J mod own_Q); own_P == 0: all
   int own_P, own_Q, own_p, own_q;

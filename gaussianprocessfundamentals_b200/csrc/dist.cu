@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(const GpbMat* __res
     const int info = (w == 0x7fffffff) ? 0 : w;
     *d.info = info;
     *d.nll = info ? nan("") : 0.5 * b + a + 0.5 * ((double)n * log2pi);
+    d.terms[0] = b; d.terms[1] = a;
   }
 }
 

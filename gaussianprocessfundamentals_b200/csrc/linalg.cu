@@ -85,7 +85,7 @@ struct GeoTrtriT {
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
     const int r0 = 2 * s * ((int)b.y + p0), rA = r0 + s;
-    if (rA >= d.n) return false;
+    if (rA >= d.n || *d.info != 0) return false;   // failed factorisation: the inverse stages do no work (grad = NaN)
     const int M = min(s, d.n - rA);
     // column tile slowest and ascending: the k-range (tj*BN .. s) shrinks with tj, so the longest tiles start first and
     // the launch drains with the short ones
@@ -112,7 +112,7 @@ struct GeoTrtriW {
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
     const int r0 = 2 * s * ((int)b.y + p0), rA = r0 + s;
-    if (rA >= d.n) return false;
+    if (rA >= d.n || *d.info != 0) return false;
     const int M = min(s, d.n - rA);
     // row tile slowest and DEscending: the k-range (0 .. (ti+1)*BM) grows with ti, longest tiles first
     const int tsn = s / BN, tsm = s / BM;
@@ -137,6 +137,7 @@ struct GeoLauum {
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
+    if (*d.info != 0) return false;
     const int Tm = (d.n + BM - 1) / BM;
     int ti, tj;
     if (!tri_map_grouped(b.x, Tm, BN / BM, 8, ti, tj)) return false;   // super-tile raster: W exceeds L2
@@ -428,6 +429,7 @@ __global__ void finalize_kernel(const GpbMat* __restrict__ mats, double log2pi) 
     double nll = 0.5 * quad + logdet + 0.5 * ((double)n * log2pi);
     if (*d.info != 0) nll = nan("");
     *d.nll = nll;
+    d.terms[0] = quad; d.terms[1] = logdet;
   }
 }
 
@@ -435,7 +437,7 @@ __global__ void finalize_kernel(const GpbMat* __restrict__ mats, double log2pi) 
 __global__ void __launch_bounds__(256) alpha_kernel(const GpbMat* __restrict__ mats) {
   const GpbMat d = mats[blockIdx.y];
   const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (col >= d.n) return;
+  if (col >= d.n || *d.info != 0) return;
   const int lane = threadIdx.x & 31;
   const double* w = d.A + (size_t)col * d.ld;
   double s = 0.0;

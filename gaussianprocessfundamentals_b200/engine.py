@@ -15,7 +15,7 @@ from .program import CompiledProgram, compile_spec, flatten_hp, unflatten_grad
 STAGE_ASSEMBLE, STAGE_POTRF, STAGE_NLL, STAGE_INVERSE, STAGE_GRAD, STAGE_BACKSOLVE = 1, 2, 4, 8, 16, 32
 STAGE_TRTRI, STAGE_LAUUM = 64, 128   # the two halves of STAGE_INVERSE
 STAGES_LML, STAGES_LML_GRAD = 7, 31
-BUF_A, BUF_KINV, BUF_ALPHA, BUF_Z, BUF_X, BUF_Y, BUF_HP, BUF_NOISE, BUF_NLL, BUF_GRAD, BUF_INFO = range(11)
+BUF_A, BUF_KINV, BUF_ALPHA, BUF_Z, BUF_X, BUF_Y, BUF_HP, BUF_NOISE, BUF_NLL, BUF_GRAD, BUF_INFO, BUF_TERMS = range(12)
 
 
 def require_cuda():
@@ -222,6 +222,37 @@ class Plan:
         off = self.grad_offsets
         grads = [gh[off[b]:off[b + 1]] for b in range(B)]
         return self._nll_h.copy(), grads, self._info_h.copy()
+
+    def set_grad_weights(self, b: int, w_quad: float, w_logdet: float):
+        """gradient of GP b = d/dtheta [w_quad * 1/2 y^T K^-1 y + w_logdet * sum(log diag L)] (default 1, 1 = the NLL)"""
+        _lib.check(self.lib.gpb_plan_set_grad_weights(self.handle, int(b), float(w_quad), float(w_logdet)),
+                   "gpb_plan_set_grad_weights")
+
+    def last_terms(self):
+        """(y^T K^-1 y [B], sum(log diag L) [B]) as copied back by the latest eval_host"""
+        quad, logdet = np.zeros(self.B), np.zeros(self.B)
+        _lib.check(self.lib.gpb_plan_last_terms(self.handle, quad.ctypes.data, logdet.ctypes.data), "gpb_plan_last_terms")
+        return quad, logdet
+
+    def host_inputs(self):
+        """([X_b views], [y_b views]) into ONE pinned host buffer laid out like the plan's input region: passing these
+        to eval_host moves the inputs of all GPs in a single host-to-device copy."""
+        if getattr(self, "_host_in", None) is None:
+            xo, yo, tot = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            offs = []
+            for b in range(self.B):
+                _lib.check(self.lib.gpb_plan_input_layout(self.handle, b, ctypes.byref(xo), ctypes.byref(yo),
+                                                          ctypes.byref(tot)), "gpb_plan_input_layout")
+                offs.append((xo.value, yo.value))
+            pinned = torch.zeros(tot.value, dtype=torch.uint8).pin_memory()
+            raw = pinned.numpy()
+            xs, ys = [], []
+            for b, (ox, oy) in enumerate(offs):
+                n, d = self.ns[b], self.programs[b].compiled.dim
+                xs.append(raw[ox:ox + 8 * n * d].view(np.float64).reshape(n, d))
+                ys.append(raw[oy:oy + 8 * n].view(np.float64))
+            self._host_in = (pinned, xs, ys)
+        return self._host_in[1], self._host_in[2]
 
     def __del__(self):
         try:

@@ -65,6 +65,7 @@ typedef struct gpb_dist gpb_dist_t;
 #define GPB_BUF_NLL 8    /* [1]                                                                      */
 #define GPB_BUF_GRAD 9   /* [n_hp + 1], last = d nll / d s2                                          */
 #define GPB_BUF_INFO 10  /* [1] int32                                                                */
+#define GPB_BUF_TERMS 11 /* [2]: y^T K^-1 y and sum(log diag L) (written by GPB_STAGE_NLL)                 */
 
 int gpb_version(void);
 const char* gpb_last_error(void);
@@ -109,6 +110,20 @@ int gpb_plan_eval(gpb_plan_t* plan, int stages, void* stream);
 int gpb_plan_eval_host(gpb_plan_t* plan, int stages, const double* const* X_host, const double* const* y_host,
                        const double* const* hp_host, const double* noise_host, double* nll_host, double* grad_host,
                        int* info_host, void* stream);
+/* Stage order.  The factorisation buffer holds K after ASSEMBLE, L after POTRF and L^-1 after TRTRI / INVERSE; a stage
+ * that needs different content than the buffer holds (POTRF twice, BACKSOLVE after the inverse, GRAD without INVERSE,
+ * NLL after the inverse of a distributed plan) is refused with -2 instead of reading garbage.                    */
+/* Weights of the two data-dependent terms of the NLL in the gradient GP b reports:
+ *   grad = d/dtheta [ w_quad * 1/2 y^T K^-1 y + w_logdet * sum(log diag L) ]          (default 1, 1: the NLL)
+ * The rank-3 BatchDataInput likelihood (Metrics/LogLikelihood.py:49,62-63 with Metrics/Metrics.py:152-154) averages the
+ * data fit over the batch but sums the log-determinant: its gradient is the sum over b with weights (1/B, 1).     */
+int gpb_plan_set_grad_weights(gpb_plan_t* plan, int b, double w_quad, double w_logdet);
+/* y^T K^-1 y and sum(log diag L) of every GP as copied back by the latest gpb_plan_eval_host (no device access) */
+int gpb_plan_last_terms(const gpb_plan_t* plan, double* quad_host, double* logdet_host);
+/* Layout of the plan's input region: X of GP b starts x_offset bytes, y of GP b y_offset bytes into a region of
+ * total_bytes.  A caller that keeps its host inputs in ONE (pinned) buffer with this layout and passes pointers into it
+ * to gpb_plan_eval_host gets a single host-to-device copy for all GPs instead of two per GP.                     */
+int gpb_plan_input_layout(const gpb_plan_t* plan, int b, size_t* x_offset, size_t* y_offset, size_t* total_bytes);
 void gpb_plan_destroy(gpb_plan_t* plan);
 
 /* ---- one large GP over a process grid (one process per GPU; NCCL over NVLink / NVSwitch) --------------------

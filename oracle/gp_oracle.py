@@ -185,6 +185,29 @@ def nll_and_grad(tree, hp_values: Sequence[np.ndarray], noise: float, x: np.ndar
     return float(val.detach().reshape(-1)[0]), g[:-1], float(np.asarray(g[-1]))
 
 
+def batch_nll(tree, hp: Sequence[torch.Tensor], noise: torch.Tensor, x: torch.Tensor, y: torch.Tensor, scaled: bool = False,
+              cp_mode: int = CP_INDICATOR, reference_distance: bool = True, reference_aggregate: bool = True):
+    """LogLikelihood.get_metric on a rank-3 BatchDataInput x [B, n, d], y [B, n, 1] (Metrics/LogLikelihood.py:30-65).
+    The data fit is per entry [B, 1, 1] (:39) but get_log_determinant_cholesky reduces over EVERY axis
+    (Metrics/Metrics.py:153-154: tf.reduce_sum without axis), so the same batch-wide log-determinant is added to every
+    entry before p_batch_metric_aggregator = tf.reduce_mean (:62-63, global_parameters.py:64) - SURVEY App. B-3.
+    reference_aggregate=False returns the mean of the true per-entry NLLs instead."""
+    n = x.shape[-2]
+    K = kernel_matrix(tree, hp, x, x, scaled, cp_mode, reference_distance)
+    Kn = K + noise * torch.eye(n, dtype=DT)
+    L = torch.linalg.cholesky(Kn)
+    z = torch.linalg.solve_triangular(L, y, upper=False)
+    alpha = torch.linalg.solve_triangular(L.transpose(-1, -2), z, upper=True)
+    data_fit = -0.5 * torch.matmul(y.transpose(-1, -2), alpha)                       # [B, 1, 1]
+    diag = torch.diagonal(L, dim1=-2, dim2=-1)                                       # tf.linalg.diag_part: [B, n]
+    if reference_aggregate:
+        logdet = 2 * torch.sum(torch.log(diag))                                      # scalar over the whole batch
+    else:
+        logdet = 2 * torch.sum(torch.log(diag), -1).reshape(-1, 1, 1)
+    ll = (data_fit + (-0.5) * logdet) + (-0.5 * (n * math.log(math.pi * 2)))
+    return -torch.mean(ll)
+
+
 def blockwise_nll(trees: Sequence, hps: Sequence[Sequence[torch.Tensor]], noise, xs, ys, **kw):
     """BlockwiseLogLikelihood.get_metric (Metrics/LogLikelihood.py:77-104): sum of per-block NLLs."""
     total = None

@@ -188,3 +188,72 @@ def test_reference_outputs_against_lapack_independent_of_torch(gold):
             assert np.max(np.abs(K - np.exp(-0.5 * (x - x.T) ** 2 / (l * l)))) <= 1e-14, name
         checked += 1
     assert checked >= 2
+
+
+# ---- round-2 goldens: rank-3 batch likelihood, partitioned K_s, blockwise metrics -------------------------------------
+@pytest.fixture(scope="module")
+def gold2():
+    z = np.load(os.path.join(os.path.dirname(GOLD), "reference_golden_r2.npz"))
+    meta = json.loads(bytes(z["__meta__"]).decode("utf-8"))
+    return z, meta
+
+
+@pytest.mark.parametrize("name", ["batch3_se", "batch3_composite"])
+def test_oracle_batch_aggregate_matches_reference(gold2, name):
+    """Metrics/LogLikelihood.py:49,62-63 + Metrics/Metrics.py:152-154: value and gradient"""
+    z, meta = gold2
+    tree = _tree(json.loads(meta[name]["spec"]))
+    flat, sizes = z[name + "/hp"], meta[name]["hp_sizes"]
+    hp, pos = [], 0
+    for sz in sizes:        # one-element vectors broadcast like the reference's rank-0 entries
+        hp.append(torch.tensor(flat[pos:pos + sz], dtype=torch.float64, requires_grad=True))
+        pos += sz
+    raw = torch.tensor(float(z[name + "/noise"]), dtype=torch.float64, requires_grad=True)
+    x, y = torch.tensor(z[name + "/x"]), torch.tensor(z[name + "/y"])
+    val = orc.batch_nll(tree, hp, raw, x, y)
+    grads = torch.autograd.grad(val, hp + [raw])
+    want = float(z[name + "/nll"][0])
+    assert abs(float(val) - want) <= 1e-12 * abs(want)
+    g = np.concatenate([t.numpy().reshape(-1) for t in grads[:-1]])
+    assert np.max(np.abs(g - z[name + "/grad"])) <= 1e-10 * np.max(np.abs(z[name + "/grad"]))
+    assert abs(float(grads[-1]) - float(z[name + "/grad_noise"][0])) <= 1e-10 * abs(float(z[name + "/grad_noise"][0]))
+    # the aggregate is NOT the mean of the per-entry likelihoods (the quirk is material)
+    per = z[name + "/per_entry_nll"]
+    assert abs(np.mean(per) - want) > 1.0
+    mean_val = orc.batch_nll(tree, [h.detach() for h in hp], raw.detach(), x, y, reference_aggregate=False)
+    assert abs(float(mean_val) - np.mean(per)) <= 1e-11 * abs(np.mean(per))
+
+
+def test_oracle_partitioned_K_s_matches_reference(gold2):
+    """block-rectangular K_s with dead rows / columns (Auxiliary/NonSquareBlockMatrices.py:8-103)"""
+    z, meta = gold2
+    for name in ("ppred_full", "ppred_dead"):
+        specs = json.loads(meta[name]["specs"])
+        sizes = meta[name]["hp_sizes"]
+        flat = z[name + "/hp"]
+        x, xt = z[name + "/x"], z[name + "/xt"]
+        edges = z[name + "/edges"]
+        Ks = z[name + "/K_s"]
+        assert Ks.shape == (x.shape[0], xt.shape[0])
+        r = c = pos = 0
+        counts = [orc.n_hp_entries(_tree(sp)) for sp in specs]
+        it = iter(sizes)
+        for i, sp in enumerate(specs):
+            lo, hi = edges[i], edges[i + 1]
+            a = np.where(np.logical_and(x[:, 0] >= lo, x[:, 0] < hi))[0]
+            b = np.where(np.logical_and(xt[:, 0] >= lo, xt[:, 0] < hi))[0]
+            assert np.array_equal(a, z[name + "/idx%d" % i]) and np.array_equal(b, z[name + "/idxt%d" % i])
+            hp = []
+            for _ in range(counts[i]):
+                sz = next(it)
+                hp.append(torch.tensor(flat[pos:pos + sz]))
+                pos += sz
+            if len(a) and len(b):
+                blk = orc.kernel_matrix(_tree(sp), hp, torch.tensor(x[a]), torch.tensor(xt[b])).numpy()
+                got = Ks[r:r + len(a), c:c + len(b)]
+                assert np.max(np.abs(got - blk)) <= 1e-13 * max(1.0, np.max(np.abs(blk)))
+                # everything outside the diagonal blocks is exactly zero
+                assert np.all(Ks[r:r + len(a), :c] == 0) and np.all(Ks[r:r + len(a), c + len(b):] == 0)
+            r += len(a)
+            c += len(b)
+        assert (r, c) == Ks.shape
