@@ -44,6 +44,7 @@ SIGNATURES = {
     "gpb_symmetrize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "gpb_dist_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "gpb_dist_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
+    "gpb_dist_loopback_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "gpb_dist_destroy": (None, [ctypes.c_void_p]),
     "gpb_plan_create_dist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
     "gpb_dist_owner": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),

@@ -598,6 +598,21 @@ int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q,
   return 0;
 }
 
+int gpb_dist_loopback_create(int world, int P, int Q, gpb_dist_t** out) {
+  if (world < 1 || world > 64) return fail_arg(1, "world out of range");
+  if (P < 1 || Q < 1 || P * Q != world || P > GPB_DIST_MAX_P) return fail_arg(2, "P x Q must equal world, P <= 8");
+  if (!out) return fail_arg(4, "out is null");
+  int rc = ensure_init();
+  if (rc) return rc;
+  std::vector<gpb::DistCtx*> ctx(world, nullptr);
+  if (gpb::dist_create_loopback(world, P, Q, ctx.data())) { g_err = gpb::dist_last_error(); return 2000; }
+  for (int r = 0; r < world; ++r) {
+    out[r] = new gpb_dist;
+    out[r]->ctx = ctx[r];
+  }
+  return 0;
+}
+
 void gpb_dist_destroy(gpb_dist_t* d) {
   if (!d) return;
   gpb::dist_destroy(d->ctx);

@@ -27,8 +27,14 @@
 #include <dlfcn.h>
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "dist.h"
 #include "gemm.cuh"
@@ -53,8 +59,9 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0;
 static NcclApi g_nccl;
-static std::string g_dist_err;
+static thread_local std::string g_dist_err;     // per host thread: the loop-back ranks run on one thread each
 const char* dist_last_error() { return g_dist_err.c_str(); }
 
 static bool nccl_load() {
@@ -84,8 +91,6 @@ static bool nccl_ok(ncclResult_t r, const char* where) {
   g_dist_err = std::string(where) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
   return false;
 }
-constexpr int NCCL_F64 = 8, NCCL_SUM = 0;
-
 int dist_unique_id(unsigned char* id128) {
   if (!nccl_load()) return 1;
   NcclId id;
@@ -94,21 +99,166 @@ int dist_unique_id(unsigned char* id128) {
   return 0;
 }
 
+// ---- transport 1: NCCL (one process per GPU) -----------------------------------------------------------------------
+struct NcclTransport : Transport {
+  void* comm = nullptr;
+  ~NcclTransport() override { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+  bool group_start() override { return nccl_ok(g_nccl.GroupStart(), "ncclGroupStart"); }
+  bool group_end() override { return nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd"); }
+  bool broadcast(const double* send, double* recv, size_t count, int root, cudaStream_t s) override {
+    return nccl_ok(g_nccl.Broadcast(send, recv, count, NCCL_F64, root, comm, s), "ncclBroadcast");
+  }
+  bool allreduce_sum(double* buf, size_t count, cudaStream_t s) override {
+    return nccl_ok(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, comm, s), "ncclAllReduce");
+  }
+};
+
 int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, DistCtx** out) {
   if (!nccl_load()) return 1;
   NcclId id;
   memcpy(id.internal, id128, 128);
   void* comm = nullptr;
   if (!nccl_ok(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank")) return 1;
+  NcclTransport* t = new NcclTransport;
+  t->comm = comm;
   DistCtx* d = new DistCtx;
-  d->comm = comm; d->rank = rank; d->world = world; d->P = P; d->Q = Q; d->p = rank / Q; d->q = rank % Q;
+  d->tr = t; d->rank = rank; d->world = world; d->P = P; d->Q = Q; d->p = rank / Q; d->q = rank % Q;
   *out = d;
+  return 0;
+}
+
+// ---- transport 2: loop-back world (virtual ranks inside one process, one device) ---------------------------------------
+// Every virtual rank is driven by its own host thread with its own plan, workspace and streams.  A collective is a host
+// rendezvous plus stream-ordered device copies: the root records an event behind its pending work and publishes its
+// buffer; each receiver makes its stream wait on that event, copies device-to-device and records a done-event; the root's
+// stream then waits on all done-events (its buffer may be overwritten afterwards).  Nothing ever spins on the device -
+// the only cross-rank dependencies are CUDA events recorded BEFORE they are waited on - so the virtual ranks cannot
+// dead-lock however the hardware interleaves their kernels.  Ranks must issue their collectives in the same order (as
+// with NCCL).
+struct LoopWorld {
+  struct Slot {
+    const double* send = nullptr;
+    cudaEvent_t ready = nullptr;
+    std::vector<cudaEvent_t> done;      // one per receiver that has enqueued its copy
+    bool posted = false;
+    int finished = 0;                   // ranks that are through with the slot
+    std::vector<const double*> contrib; // all-reduce: staged contribution of every rank
+    std::vector<cudaEvent_t> contrib_ready;
+    double* staging = nullptr;
+    int arrived = 0;
+  };
+  int world;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::map<long long, Slot> slots;      // collective sequence number -> rendezvous state
+  std::vector<double*> stagings;        // freed with the world
+  explicit LoopWorld(int w) : world(w) {}
+  ~LoopWorld() { for (double* p : stagings) cudaFree(p); }
+};
+
+__global__ void loop_sum_kernel(double* __restrict__ dst, const double* __restrict__ staging, int world, size_t count) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double s = 0.0;
+  for (int r = 0; r < world; ++r) s += staging[(size_t)r * count + i];   // rank order: every rank gets the same bits
+  dst[i] = s;
+}
+
+struct LoopTransport : Transport {
+  std::shared_ptr<LoopWorld> w;
+  int rank = 0;
+  long long seq = 0;
+  bool fail(cudaError_t e, const char* where) {
+    g_dist_err = std::string("loop-back ") + where + ": " + cudaGetErrorString(e);
+    return false;
+  }
+  // a rank that failed (or a caller that did not start every rank) must not hang the others for ever
+  template <class Pred>
+  bool wait_for(std::unique_lock<std::mutex>& lk, Pred pred) {
+    if (w->cv.wait_for(lk, std::chrono::seconds(120), pred)) return true;
+    g_dist_err = "loop-back rendezvous timed out: not every virtual rank issued this collective";
+    return false;
+  }
+  bool group_start() override { return true; }
+  bool group_end() override { return true; }
+  bool broadcast(const double* send, double* recv, size_t count, int root, cudaStream_t s) override {
+    const long long id = seq++;
+    cudaError_t e;
+    std::unique_lock<std::mutex> lk(w->mu);
+    LoopWorld::Slot& sl = w->slots[id];
+    if (rank == root) {
+      if ((e = cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+      if ((e = cudaEventRecord(sl.ready, s)) != cudaSuccess) return fail(e, "record");
+      sl.send = send; sl.posted = true;
+      w->cv.notify_all();
+      if (!wait_for(lk, [&] { return (int)sl.done.size() == w->world - 1; })) return false;
+      for (cudaEvent_t ev : sl.done)
+        if ((e = cudaStreamWaitEvent(s, ev, 0)) != cudaSuccess) return fail(e, "wait(done)");
+      if (send != recv && count)
+        if ((e = cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return fail(e, "copy");
+    } else {
+      if (!wait_for(lk, [&] { return sl.posted; })) return false;
+      if ((e = cudaStreamWaitEvent(s, sl.ready, 0)) != cudaSuccess) return fail(e, "wait(ready)");
+      if (count)
+        if ((e = cudaMemcpyAsync(recv, sl.send, count * sizeof(double), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return fail(e, "copy");
+      cudaEvent_t dn;
+      if ((e = cudaEventCreateWithFlags(&dn, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+      if ((e = cudaEventRecord(dn, s)) != cudaSuccess) return fail(e, "record");
+      sl.done.push_back(dn);
+      w->cv.notify_all();
+    }
+    if (++sl.finished == w->world) {          // events may be destroyed while work is pending: freed on completion
+      if (sl.ready) cudaEventDestroy(sl.ready);
+      for (cudaEvent_t ev : sl.done) cudaEventDestroy(ev);
+      w->slots.erase(id);
+    }
+    return true;
+  }
+  bool allreduce_sum(double* buf, size_t count, cudaStream_t s) override {
+    const long long id = seq++;
+    cudaError_t e;
+    std::unique_lock<std::mutex> lk(w->mu);
+    LoopWorld::Slot& sl = w->slots[id];
+    if (!sl.staging) {
+      if ((e = cudaMalloc(&sl.staging, (size_t)w->world * count * sizeof(double))) != cudaSuccess) return fail(e, "staging");
+      w->stagings.push_back(sl.staging);
+      sl.contrib_ready.assign(w->world, nullptr);
+    }
+    if ((e = cudaMemcpyAsync(sl.staging + (size_t)rank * count, buf, count * sizeof(double), cudaMemcpyDeviceToDevice, s)) != cudaSuccess)
+      return fail(e, "stage");
+    if ((e = cudaEventCreateWithFlags(&sl.contrib_ready[rank], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaEventRecord(sl.contrib_ready[rank], s)) != cudaSuccess) return fail(e, "record");
+    ++sl.arrived;
+    w->cv.notify_all();
+    if (!wait_for(lk, [&] { return sl.arrived == w->world; })) return false;
+    for (int r = 0; r < w->world; ++r)
+      if (r != rank && (e = cudaStreamWaitEvent(s, sl.contrib_ready[r], 0)) != cudaSuccess) return fail(e, "wait(contrib)");
+    loop_sum_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(buf, sl.staging, w->world, count);
+    ++g_launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "sum");
+    if (++sl.finished == w->world) {
+      for (cudaEvent_t ev : sl.contrib_ready) if (ev) cudaEventDestroy(ev);
+      w->slots.erase(id);                      // the staging buffer stays alive until the world is destroyed
+    }
+    return true;
+  }
+};
+
+int dist_create_loopback(int world, int P, int Q, DistCtx** out) {
+  auto w = std::make_shared<LoopWorld>(world);
+  for (int r = 0; r < world; ++r) {
+    LoopTransport* t = new LoopTransport;
+    t->w = w; t->rank = r;
+    DistCtx* d = new DistCtx;
+    d->tr = t; d->rank = r; d->world = world; d->P = P; d->Q = Q; d->p = r / Q; d->q = r % Q;
+    out[r] = d;
+  }
   return 0;
 }
 
 void dist_destroy(DistCtx* d) {
   if (!d) return;
-  if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+  delete d->tr;
   delete d;
 }
 
@@ -260,7 +410,7 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(const GpbMat* __res
 }
 
 #define GPB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
-#define GPB_NK(x, where) do { if (!nccl_ok((x), where)) return cudaErrorUnknown; } while (0)
+#define GPB_TR(x) do { if (!(x)) return cudaErrorUnknown; } while (0)
 
 template <class Cfg, class Geo>
 static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
@@ -326,11 +476,11 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
         tile_copy_kernel<<<8, 256, 0, cs>>>(st_wd, Wk);
         g_launches += 2;
       }
-      GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
-      GPB_NK(g_nccl.Broadcast(st + (size_t)map.seg_base[pk] * TILE_ELEMS, st + (size_t)map.seg_base[pk] * TILE_ELEMS,
-                              TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(diag)");
-      GPB_NK(g_nccl.Broadcast(st_wd, st_wd, TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(inv diag)");
-      GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+      GPB_TR(D.tr->group_start());
+      GPB_TR(D.tr->broadcast(st + (size_t)map.seg_base[pk] * TILE_ELEMS, st + (size_t)map.seg_base[pk] * TILE_ELEMS,
+                             TILE_ELEMS, diag_owner, cs));
+      GPB_TR(D.tr->broadcast(st_wd, st_wd, TILE_ELEMS, diag_owner, cs));
+      GPB_TR(D.tr->group_end());
       if (D.rank != diag_owner) {
         panel_copy_kernel<<<1, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, 0, st, map, p, qk, q, 1);
         tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd);
@@ -350,17 +500,16 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
         ++g_launches;
       }
       if (ship_wd && D.rank == diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(st_wd, Wk); ++g_launches; }
-      GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
-      if (ship_wd)
-        GPB_NK(g_nccl.Broadcast(st_wd, st_wd, TILE_ELEMS, NCCL_F64, diag_owner, D.comm, cs), "ncclBroadcast(inv diag)");
+      GPB_TR(D.tr->group_start());
+      if (ship_wd) GPB_TR(D.tr->broadcast(st_wd, st_wd, TILE_ELEMS, diag_owner, cs));
       for (int o = 0; o < P; ++o) {
         int first = seg_base[o], cnt = seg_count[o];
         if (t0 == 1 && o == pk) { first += 1; cnt -= 1; }  // skip the diagonal tile (slot 0 of its owner's segment)
         if (cnt <= 0) continue;
         double* b = st + (size_t)first * TILE_ELEMS;
-        GPB_NK(g_nccl.Broadcast(b, b, (size_t)cnt * TILE_ELEMS, NCCL_F64, o * Q + qk, D.comm, cs), "ncclBroadcast(panel)");
+        GPB_TR(D.tr->broadcast(b, b, (size_t)cnt * TILE_ELEMS, o * Q + qk, cs));
       }
-      GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+      GPB_TR(D.tr->group_end());
       panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 1);
       ++g_launches;
       if (ship_wd && D.rank != diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd); ++g_launches; }
@@ -564,13 +713,12 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   }
   // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
   for (int J0 = 0; J0 < nblk; J0 += 64) {
-    GPB_NK(g_nccl.GroupStart(), "ncclGroupStart");
+    GPB_TR(D.tr->group_start());
     for (int J = J0; J < std::min(nblk, J0 + 64); ++J) {
       const int cols = std::min(GPB_NB, n - J * GPB_NB);
-      GPB_NK(g_nccl.Broadcast(h.Kinv + (size_t)J * GPB_NB * ld, h.A + (size_t)J * GPB_NB * ld, (size_t)cols * ld, NCCL_F64,
-                              J % world, D.comm, s), "ncclBroadcast(W)");
+      GPB_TR(D.tr->broadcast(h.Kinv + (size_t)J * GPB_NB * ld, h.A + (size_t)J * GPB_NB * ld, (size_t)cols * ld, J % world, s));
     }
-    GPB_NK(g_nccl.GroupEnd(), "ncclGroupEnd");
+    GPB_TR(D.tr->group_end());
   }
   return cudaSuccess;
 }
@@ -584,7 +732,7 @@ cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
 }
 
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s) {
-  GPB_NK(g_nccl.AllReduce(grad, grad, (size_t)count, NCCL_F64, NCCL_SUM, D.comm, s), "ncclAllReduce(grad)");
+  GPB_TR(D.tr->allreduce_sum(grad, (size_t)count, s));
   return cudaSuccess;
 }
 

@@ -8,14 +8,28 @@
 
 namespace gpb {
 
+// The exchange steps of the distributed stages go through a transport so that the SAME ownership, packing and launch
+// code runs over NCCL (one process per GPU) and over the loop-back world (all ranks of a virtual P x Q grid inside one
+// process on one device, each driven by its own host thread - how a single-GPU CI box exercises the distributed path).
+struct Transport {
+  virtual ~Transport() {}
+  virtual bool group_start() = 0;
+  virtual bool group_end() = 0;
+  // `count` doubles from rank `root` into `recv` of every rank (send == recv: in place); ordered on `s`
+  virtual bool broadcast(const double* send, double* recv, size_t count, int root, cudaStream_t s) = 0;
+  virtual bool allreduce_sum(double* buf, size_t count, cudaStream_t s) = 0;   // in place
+};
+
 struct DistCtx {
-  void* comm;                 // ncclComm_t
+  Transport* tr;              // owned
   int rank, world, P, Q, p, q;  // rank = p * Q + q
 };
 
 const char* dist_last_error();
 int dist_unique_id(unsigned char* id128);
 int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, DistCtx** out);
+// `world` contexts of one loop-back world (virtual ranks 0 .. world-1 on the current device); out[world]
+int dist_create_loopback(int world, int P, int Q, DistCtx** out);
 void dist_destroy(DistCtx* d);
 void dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
 size_t dist_stage_bytes(int n);

@@ -305,6 +305,64 @@ class ProcessGrid:
             pass
 
 
+class VirtualGrid:
+    """A P x Q grid of VIRTUAL ranks on the current device (gpb_dist_loopback_create): every rank is a ProcessGrid-like
+    handle for Plan(..., grid=...).  `run(fn)` calls fn(rank, grid_handle) on one host thread per rank, each inside its
+    own CUDA stream, and returns the results in rank order - the calling convention of the distributed plan (every rank
+    makes the same calls in the same order) on a single GPU.  Used by the one-GPU tests of the distributed path."""
+
+    class _Rank:
+        def __init__(self, handle, rank, world, P, Q):
+            self.handle, self.rank, self.world, self.P, self.Q = handle, rank, world, P, Q
+            self.p, self.q = rank // Q, rank % Q
+
+        def owner(self, I: int, J: int) -> int:
+            return (I % self.P) * self.Q + (J % self.Q)
+
+    def __init__(self, P: int, Q: int):
+        require_cuda()
+        lib = _lib.load()
+        self.P, self.Q, self.world = int(P), int(Q), int(P) * int(Q)
+        handles = (ctypes.c_void_p * self.world)()
+        _lib.check(lib.gpb_dist_loopback_create(self.world, self.P, self.Q, handles), "gpb_dist_loopback_create")
+        self.ranks = [self._Rank(ctypes.c_void_p(handles[r]), r, self.world, self.P, self.Q) for r in range(self.world)]
+        self.streams = [torch.cuda.Stream() for _ in range(self.world)]
+
+    def run(self, fn):
+        import threading
+        out, err = [None] * self.world, [None] * self.world
+        dev = torch.cuda.current_device()
+
+        def work(r):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(self.streams[r]):
+                    out[r] = fn(r, self.ranks[r])
+                    self.streams[r].synchronize()
+            except BaseException as exc:   # surfaced on the calling thread
+                err[r] = exc
+        torch.cuda.synchronize()
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def __del__(self):
+        try:
+            if _lib._lib is not None:
+                for rk in getattr(self, "ranks", []):
+                    if rk.handle is not None:
+                        _lib._lib.gpb_dist_destroy(rk.handle)
+                        rk.handle = None
+        except Exception:
+            pass
+
+
 def gemm(a_kmajor: bool, b_kmajor: bool, A: torch.Tensor, lda: int, Bm: torch.Tensor, ldb: int, C: torch.Tensor,
          ldc: int, M: int, N: int, K: int, alpha: float, beta: float):
     lib = _lib.load()

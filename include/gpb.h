@@ -142,6 +142,13 @@ void gpb_plan_destroy(gpb_plan_t* plan);
  *   stage mask (collective: every rank must make the same calls in the same order).                              */
 int gpb_dist_unique_id(unsigned char* id128);
 int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q, gpb_dist_t** out);
+/* The same distributed plan over a LOOP-BACK world: `world` virtual ranks of a P x Q grid inside one process on the
+ * current device (out[world] handles, rank r = out[r]).  Each virtual rank gets its own plan (gpb_plan_create_dist), its
+ * own workspace and must be driven by its own host thread on its own stream, all ranks making the same calls in the
+ * same order - exactly as with NCCL.  The collectives become stream-ordered device copies, everything else (block
+ * ownership, panel packing, launch schedule, gradient split) is the code the NCCL path runs: this is how a one-GPU test
+ * box exercises the distributed path (the "virtual grid" of SURVEY section 4).                                  */
+int gpb_dist_loopback_create(int world, int P, int Q, gpb_dist_t** out);
 void gpb_dist_destroy(gpb_dist_t* dist);
 int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out);
 /* host arithmetic of the layout (no GPU needed): owner rank of block (I, J); staging order of the n_tiles blocks of
