@@ -455,7 +455,9 @@ def run_batch(ctx, key, steps, warmup, cpu_leg):
     args, rank, world = ctx.args, ctx.rank, ctx.world
     w = WORKLOADS[key]
     trees, hps, ns, xs, ys = build_workload(key, rank, world)
-    progs = [eng.DeviceProgram.get(t, 1, False, 1) for t in trees]
+    t_jit = time.perf_counter()
+    progs = eng.DeviceProgram.get_many(trees, 1, False, 1)      # kernels specialised per program: compiled in parallel
+    t_jit = time.perf_counter() - t_jit
     plan = eng.Plan(progs, ns, want_grad=True)
     for b in range(len(ns)):
         plan.set_data(b, torch.tensor(xs[b]), torch.tensor(ys[b]))
@@ -594,6 +596,11 @@ def run_batch(ctx, key, steps, warmup, cpu_leg):
                      "inverse_tflops": tf_inv, "inverse_frac": tf_inv / peak},
         "check": {"nll0": float(nll[0]), "info_max": int(np.max(info)),
                   "e2e_matches_resident": bool(abs(nll_h[0] - nll[0]) <= 1e-12 * abs(nll[0]))},
+        # assembly and trace gradient run on kernels generated per kernel program and compiled at program creation
+        # (csrc/jit.cu, NVRTC); set-up cost, outside the timed region like the plan construction
+        "specialised_kernels": {"programs": len(set(id(p_) for p_ in progs)),
+                                "specialised": int(sum(1 for p_ in set(progs) if p_.specialised)),
+                                "create_s": round(t_jit, 3)},
     }
     if cpu_leg:
         rec["cpu_baseline"] = cpu_baseline(key)

@@ -22,8 +22,13 @@ class DeviceBlocks:
         self.ns = [int(x.shape[0]) for x in xs]
         scaled = bool(global_param.p_scaled_base_kernel)
         cp_mode = global_param.cp_mode_code()
-        self.programs = [engine.DeviceProgram.get(kern.to_spec(), kern.get_dimensionality(), scaled, cp_mode)
-                         for kern in self.kernels]
+        dims = {kern.get_dimensionality() for kern in self.kernels}
+        if len(dims) == 1:      # programs that do not exist yet are compiled in parallel
+            self.programs = engine.DeviceProgram.get_many([kern.to_spec() for kern in self.kernels], dims.pop(), scaled,
+                                                          cp_mode)
+        else:
+            self.programs = [engine.DeviceProgram.get(kern.to_spec(), kern.get_dimensionality(), scaled, cp_mode)
+                             for kern in self.kernels]
         self.key = (tuple(p.compiled.signature() for p in self.programs), tuple(self.ns), scaled, cp_mode, want_grad)
         self.plan = engine.Plan(self.programs, self.ns, want_grad=want_grad, grid=grid)
         self.want_grad = want_grad

@@ -20,6 +20,14 @@ SIGNATURES = {
     "gpb_program_create": (ctypes.c_int, [c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "gpb_program_num_hp": (ctypes.c_int, [ctypes.c_void_p]),
     "gpb_program_destroy": (None, [ctypes.c_void_p]),
+    "gpb_program_is_specialised": (ctypes.c_int, [ctypes.c_void_p]),
+    "gpb_program_jit_note": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gpb_jit_available": (ctypes.c_int, []),
+    "gpb_jit_set_nvrtc_path": (ctypes.c_int, [ctypes.c_char_p]),
+    "gpb_jit_source": (ctypes.c_int, [c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t,
+                                      ctypes.POINTER(ctypes.c_size_t)]),
+    "gpb_jit_cubin": (ctypes.c_int, [c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p,
+                                     ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "gpb_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                     ctypes.c_void_p]),

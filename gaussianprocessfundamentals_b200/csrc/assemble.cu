@@ -86,8 +86,8 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   }
 }
 
-__global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __restrict__ mats) {
-  const GpbMat& d = mats[blockIdx.z];
+__global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __restrict__ mats, const int* __restrict__ which) {
+  const GpbMat& d = mats[which ? which[blockIdx.z] : blockIdx.z];
   const int T = (d.n + A_T - 1) / A_T;
   int ti, tj;
   if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
@@ -125,9 +125,9 @@ struct SmemAcc {
   __device__ __forceinline__ void operator()(int p, double v) const { base[p * 256] += v; }
 };
 
-__global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ mats, int acc_stride) {
+__global__ void __launch_bounds__(256) grad_kernel(const GpbMat* __restrict__ mats, const int* __restrict__ which, int acc_stride) {
   extern __shared__ __align__(16) unsigned char g_smem[];
-  const GpbMat& d = mats[blockIdx.z];
+  const GpbMat& d = mats[which ? which[blockIdx.z] : blockIdx.z];
   const int T = (d.n + A_T - 1) / A_T;
   int ti, tj;
   if (!tri_map(blockIdx.x, T, 1, 0, T, ti, tj)) return;
@@ -233,10 +233,11 @@ cudaError_t assemble_init() {
   return cudaSuccess;
 }
 
-cudaError_t run_assemble_batched(const GpbMat* dm, int B, int n_max, cudaStream_t s) {
+// the GPs which[0 .. B) of the descriptor array (which == nullptr: the first B) on the interpreter kernels
+cudaError_t run_assemble_batched(const GpbMat* dm, const int* which, int B, int n_max, cudaStream_t s) {
   const int T = (n_max + A_T - 1) / A_T;
   const size_t smem = asm_smem_bytes(GPB_MAX_OPS, GPB_MAX_HP, GPB_MAX_DIM);
-  assemble_batched_kernel<<<dim3((unsigned)tri_count(T, 1, 0, T), 1, B), 256, smem, s>>>(dm);
+  assemble_batched_kernel<<<dim3((unsigned)tri_count(T, 1, 0, T), 1, B), 256, smem, s>>>(dm, which);
   ++g_launches;
   return cudaGetLastError();
 }
@@ -258,12 +259,18 @@ cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int c
   return cudaGetLastError();
 }
 
-cudaError_t run_grad(const GpbMat* dm, int B, int n_max, int n_hp_max, int n_ops_max, int dim, cudaStream_t s) {
+// per-tile partial sums of the gradient for the GPs which[0 .. B) on the interpreter kernel
+cudaError_t run_grad_tiles(const GpbMat* dm, const int* which, int B, int n_max, int n_hp_max, int n_ops_max, int dim,
+                           cudaStream_t s) {
   const int tiles = grad_tiles(n_max);
   const size_t smem = grad_smem_bytes(n_ops_max, n_hp_max, dim);
-  grad_kernel<<<dim3(tiles, 1, B), 256, smem, s>>>(dm, n_hp_max + 1);
+  grad_kernel<<<dim3(tiles, 1, B), 256, smem, s>>>(dm, which, n_hp_max + 1);
   ++g_launches;
-  GPB_CK(cudaGetLastError());
+  return cudaGetLastError();
+}
+
+// second stage for ALL B GPs of the plan (the partial sums may come from interpreter and specialised kernels alike)
+cudaError_t run_grad_reduce(const GpbMat* dm, int B, int n_hp_max, cudaStream_t s) {
   grad_reduce_kernel<<<dim3((n_hp_max + 1 + 7) / 8, B), 256, 0, s>>>(dm);
   ++g_launches;
   return cudaGetLastError();

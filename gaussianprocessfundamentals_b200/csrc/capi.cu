@@ -3,12 +3,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/gpb.h"
 #include "dist.h"
 #include "internal.h"
+#include "jit.h"
 #include "program.cuh"
 
 namespace gpb {
@@ -26,8 +28,10 @@ static int fail_cuda(cudaError_t e, const char* where) {
 }
 #define CU(x, where) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, where); } while (0)
 
+static std::mutex g_init_mu;
 static bool g_inited = false;
-static int ensure_init() {
+static int ensure_init() {      // programs are created from several host threads (run-time compilation in parallel)
+  std::lock_guard<std::mutex> lk(g_init_mu);
   if (g_inited) return 0;
   CU(gpb::linalg_init(), "linalg_init");
   CU(gpb::assemble_init(), "assemble_init");
@@ -36,10 +40,50 @@ static int ensure_init() {
 }
 
 struct gpb_program {
-  int n_ops, dim, cp_mode, n_hp;
+  int n_ops, dim, cp_mode, n_hp, tape;
   std::vector<int32_t> code;
   int32_t* code_dev;
+  gpb::JitKernels jit;      // kernels specialised for this program (null: interpreter)
+  std::string jit_note;     // why not, when not
 };
+
+// structural checks of a postfix program; n_hp, gradient-tape length and stack depth it needs
+static int check_program(const int32_t* code, int n_ops, int dim, int cp_mode, int* n_hp_out, int* tape_out, int* depth_out) {
+  if (!code) return fail_arg(1, "code is null");
+  if (n_ops <= 0 || n_ops > GPB_MAX_OPS) return fail_arg(2, "n_ops out of range");
+  if (dim < 1 || dim > GPB_MAX_DIM) return fail_arg(3, "dim out of range");
+  if (cp_mode < 0 || cp_mode > 2) return fail_arg(4, "cp_mode out of range");
+  int sp = 0, tape = 0, max_sp = 0, n_hp = 0;
+  for (int pc = 0; pc < n_ops; ++pc) {
+    const int32_t* w = code + pc * GPB_OP_WORDS;
+    const int op = w[0];
+    if (op >= GPB_OP_SE && op <= GPB_OP_L1) {
+      const int nq = gpb_leaf_nhp(op, w[2], dim);
+      if (w[1] < 0) return fail_arg(1, "negative hyper-parameter offset");
+      if (w[1] + nq > n_hp) n_hp = w[1] + nq;
+      tape += nq;
+      ++sp;
+    } else if (op == GPB_OP_ADD2 || op == GPB_OP_MUL2) {
+      if (sp < 2) return fail_arg(1, "stack underflow");
+      --sp;
+      if (op == GPB_OP_MUL2) tape += 2;
+    } else if (op == GPB_OP_CPW) {
+      if (sp < 1) return fail_arg(1, "stack underflow");
+      if (dim != 1) return fail_arg(3, "change-point operators need 1-d inputs (Operators.py:398)");
+      if (w[3] < 2 || w[2] < 0 || w[2] >= w[3]) return fail_arg(1, "bad change-point child index");
+      if (w[1] < 0) return fail_arg(1, "negative hyper-parameter offset");
+      if (w[1] + w[3] - 1 > n_hp) n_hp = w[1] + w[3] - 1;
+      tape += 4;
+    } else {
+      return fail_arg(1, "unknown opcode");
+    }
+    if (sp > max_sp) max_sp = sp;
+  }
+  if (sp != 1) return fail_arg(1, "program does not leave exactly one value");
+  if (n_hp > GPB_MAX_HP) return fail_arg(1, "too many hyper-parameters");
+  *n_hp_out = n_hp; *tape_out = tape; *depth_out = max_sp;
+  return 0;
+}
 
 enum { NBUF = 12 };
 enum { HOLDS_NONE = 0, HOLDS_K = 1, HOLDS_L = 2, HOLDS_W = 3 };
@@ -60,6 +104,9 @@ struct gpb_plan {
   int holds;                     // what GPB_BUF_A currently holds (HOLDS_*): stages are checked against it
   int have_kinv;                 // GPB_BUF_KINV holds inv(K) of the current factorisation
   std::vector<double> gw;        // [2 B] gradient weights (quad, logdet) per GP
+  // GPs that share a kernel program are assembled / differentiated by one launch of that program's kernels
+  struct Group { const gpb_program* prog; std::vector<int> idx; int n_max; size_t off_which; };
+  std::vector<Group> groups;
   std::vector<size_t> hp_prefix, grad_prefix;
   char* ws;
   int n_max, n_hp_max, n_ops_max, dim;
@@ -120,50 +167,78 @@ const char* gpb_last_error(void) { return g_err.c_str(); }
 long long gpb_launch_count(void) { return gpb::g_launches.load(); }
 
 int gpb_program_create(const int32_t* code, int n_ops, int dim, int cp_mode, gpb_program_t** out) {
-  if (!code) return fail_arg(1, "code is null");
-  if (n_ops <= 0 || n_ops > GPB_MAX_OPS) return fail_arg(2, "n_ops out of range");
-  if (dim < 1 || dim > GPB_MAX_DIM) return fail_arg(3, "dim out of range");
-  if (cp_mode < 0 || cp_mode > 2) return fail_arg(4, "cp_mode out of range");
   if (!out) return fail_arg(5, "out is null");
-  int sp = 0, tape = 0, max_sp = 0, n_hp = 0;
-  for (int pc = 0; pc < n_ops; ++pc) {
-    const int32_t* w = code + pc * GPB_OP_WORDS;
-    const int op = w[0];
-    if (op >= GPB_OP_SE && op <= GPB_OP_L1) {
-      const int nq = gpb_leaf_nhp(op, w[2], dim);
-      if (w[1] < 0) return fail_arg(1, "negative hyper-parameter offset");
-      if (w[1] + nq > n_hp) n_hp = w[1] + nq;
-      tape += nq;
-      ++sp;
-    } else if (op == GPB_OP_ADD2 || op == GPB_OP_MUL2) {
-      if (sp < 2) return fail_arg(1, "stack underflow");
-      --sp;
-      if (op == GPB_OP_MUL2) tape += 2;
-    } else if (op == GPB_OP_CPW) {
-      if (sp < 1) return fail_arg(1, "stack underflow");
-      if (dim != 1) return fail_arg(3, "change-point operators need 1-d inputs (Operators.py:398)");
-      if (w[3] < 2 || w[2] < 0 || w[2] >= w[3]) return fail_arg(1, "bad change-point child index");
-      if (w[1] + w[3] - 1 > n_hp) n_hp = w[1] + w[3] - 1;
-      tape += 4;
-    } else {
-      return fail_arg(1, "unknown opcode");
-    }
-    if (sp > max_sp) max_sp = sp;
-  }
-  if (sp != 1) return fail_arg(1, "program does not leave exactly one value");
-  if (max_sp > GPB_MAX_STACK) return fail_arg(1, "operand stack too deep");
-  if (tape > GPB_MAX_TAPE) return fail_arg(1, "gradient tape too long");
-  if (n_hp > GPB_MAX_HP) return fail_arg(1, "too many hyper-parameters");
-  int rc = ensure_init();
+  int n_hp = 0, tape = 0, depth = 0;
+  int rc = check_program(code, n_ops, dim, cp_mode, &n_hp, &tape, &depth);
+  if (rc) return rc;
+  // the value-only interpreter (rectangular assembly: K_s, K_ss, get_K) keeps its operand stack in 8 registers
+  if (depth > GPB_MAX_STACK) return fail_arg(1, "operand stack too deep");
+  rc = ensure_init();
   if (rc) return rc;
   gpb_program* p = new gpb_program;
-  p->n_ops = n_ops; p->dim = dim; p->cp_mode = cp_mode; p->n_hp = n_hp;
+  p->n_ops = n_ops; p->dim = dim; p->cp_mode = cp_mode; p->n_hp = n_hp; p->tape = tape;
   p->code.assign(code, code + (size_t)n_ops * GPB_OP_WORDS);
   p->code_dev = nullptr;
+  // kernels specialised for this program (assembly + trace gradient of the plans); the interpreter stays the fallback
+  std::string why;
+  if (gpb::jit_build(code, n_ops, dim, cp_mode, n_hp, p->jit, why)) p->jit_note = why;
+  if (!p->jit.grad && tape > GPB_MAX_TAPE) {
+    g_err = "gradient tape of " + std::to_string(tape) + " entries exceeds the interpreter's " + std::to_string(GPB_MAX_TAPE) +
+            " and no specialised kernel could be built: " + why;
+    delete p;
+    return -1;
+  }
   cudaError_t e = cudaMalloc(&p->code_dev, p->code.size() * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMemcpy(p->code_dev, p->code.data(), p->code.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { if (p->code_dev) cudaFree(p->code_dev); delete p; return fail_cuda(e, "gpb_program_create"); }
+  if (e != cudaSuccess) {
+    if (p->code_dev) cudaFree(p->code_dev);
+    gpb::jit_release(p->jit);
+    delete p;
+    return fail_cuda(e, "gpb_program_create");
+  }
   *out = p;
+  return 0;
+}
+
+int gpb_program_is_specialised(const gpb_program_t* prog) { return (prog && prog->jit.grad) ? 1 : 0; }
+
+const char* gpb_program_jit_note(const gpb_program_t* prog) { return prog ? prog->jit_note.c_str() : ""; }
+
+int gpb_jit_available(void) { return gpb::jit_enabled(nullptr) ? 1 : 0; }
+
+int gpb_jit_set_nvrtc_path(const char* path) {
+  gpb::jit_set_nvrtc_path(path);
+  return 0;
+}
+
+int gpb_jit_source(const int32_t* code, int n_ops, int dim, int cp_mode, char* buf, size_t capacity, size_t* needed) {
+  int n_hp = 0, tape = 0, depth = 0;
+  int rc = check_program(code, n_ops, dim, cp_mode, &n_hp, &tape, &depth);
+  if (rc) return rc;
+  std::string src, err;
+  if (gpb::jit_generate(code, n_ops, dim, cp_mode, n_hp, src, err)) { g_err = err; return -1; }
+  if (needed) *needed = src.size() + 1;
+  if (buf && capacity > 0) {
+    const size_t k = src.size() + 1 <= capacity ? src.size() : capacity - 1;
+    memcpy(buf, src.data(), k);
+    buf[k] = 0;
+  }
+  return 0;
+}
+
+int gpb_jit_cubin(const int32_t* code, int n_ops, int dim, int cp_mode, const char* arch, void* buf, size_t capacity,
+                  size_t* needed) {
+  if (!arch) return fail_arg(5, "arch is null");
+  int n_hp = 0, tape = 0, depth = 0;
+  int rc = check_program(code, n_ops, dim, cp_mode, &n_hp, &tape, &depth);
+  if (rc) return rc;
+  std::string src, err;
+  if (gpb::jit_generate(code, n_ops, dim, cp_mode, n_hp, src, err)) { g_err = err; return -1; }
+  std::vector<char> cubin;
+  std::string log;
+  if (gpb::jit_compile(src, arch, cubin, log)) { g_err = log; return 3000; }
+  if (needed) *needed = cubin.size();
+  if (buf && capacity >= cubin.size()) memcpy(buf, cubin.data(), cubin.size());
   return 0;
 }
 
@@ -171,6 +246,7 @@ int gpb_program_num_hp(const gpb_program_t* prog) { return prog ? prog->n_hp : -
 
 void gpb_program_destroy(gpb_program_t* prog) {
   if (!prog) return;
+  gpb::jit_release(prog->jit);
   if (prog->code_dev) cudaFree(prog->code_dev);
   delete prog;
 }
@@ -267,6 +343,14 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   if (dist) {
     for (int i = 0; i < 2; ++i) { p->off_stage[i] = off; off = al(off + gpb::dist_stage_bytes((int)n[0])); }
   }
+  for (int b = 0; b < B; ++b) {
+    gpb_plan::Group* g = nullptr;
+    for (auto& q : p->groups) if (q.prog == progs[b]) { g = &q; break; }
+    if (!g) { p->groups.push_back(gpb_plan::Group{progs[b], {}, 0, 0}); g = &p->groups.back(); }
+    g->idx.push_back(b);
+    if ((int)n[b] > g->n_max) g->n_max = (int)n[b];
+  }
+  for (auto& g : p->groups) { g.off_which = off; off = al(off + g.idx.size() * sizeof(int)); }
   p->ws_bytes = off;
   p->h_in = nullptr; p->h_out = nullptr;
   cudaError_t e = cudaMallocHost(&p->h_in, p->in_bytes + 16);
@@ -355,6 +439,8 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
   p->holds = HOLDS_NONE; p->have_kinv = 0;
   CU(cudaMemcpy(p->ws + p->off_desc, h.data(), (size_t)p->B * sizeof(GpbMat), cudaMemcpyHostToDevice), "gpb_plan_bind");
   CU(cudaMemset(p->ws + p->off_out, 0, p->out_bytes), "gpb_plan_bind");
+  for (const auto& g : p->groups)
+    CU(cudaMemcpy(p->ws + g.off_which, g.idx.data(), g.idx.size() * sizeof(int), cudaMemcpyHostToDevice), "gpb_plan_bind");
   return 0;
 }
 
@@ -370,6 +456,29 @@ int gpb_plan_buffer(const gpb_plan_t* p, int b, int which, void** ptr, size_t* b
   return 0;
 }
 
+// assembly / gradient of all GPs of the plan: one launch per kernel program (its specialised kernels, else the interpreter)
+static cudaError_t plan_assemble(gpb_plan* p, const GpbMat* dm, cudaStream_t s) {
+  for (const auto& g : p->groups) {
+    const int* which = (const int*)(p->ws + g.off_which);
+    const int T = (g.n_max + 63) / 64;
+    cudaError_t e;
+    if (g.prog->jit.assemble) e = gpb::jit_launch(g.prog->jit.assemble, (unsigned)(T * (T + 1) / 2), (unsigned)g.idx.size(), dm, which, s);
+    else e = gpb::run_assemble_batched(dm, which, (int)g.idx.size(), g.n_max, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+static cudaError_t plan_grad(gpb_plan* p, const GpbMat* dm, cudaStream_t s) {
+  for (const auto& g : p->groups) {
+    const int* which = (const int*)(p->ws + g.off_which);
+    cudaError_t e;
+    if (g.prog->jit.grad) e = gpb::jit_launch(g.prog->jit.grad, (unsigned)gpb::grad_tiles(g.n_max), (unsigned)g.idx.size(), dm, which, s);
+    else e = gpb::run_grad_tiles(dm, which, (int)g.idx.size(), g.n_max, g.prog->n_hp, g.prog->n_ops, p->dim, s);
+    if (e != cudaSuccess) return e;
+  }
+  return gpb::run_grad_reduce(dm, p->B, p->n_hp_max, s);
+}
+
 int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   if (!p) return fail_arg(1, "plan is null");
   if (!p->ws) return fail_arg(1, "plan is not bound");
@@ -383,7 +492,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
 
     if (stages & GPB_STAGE_ASSEMBLE) {
       CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
-      CU(gpb::run_assemble_batched(dm, 1, p->n_max, s), "assemble");
+      CU(plan_assemble(p, dm, s), "assemble");
     }
     if (stages & GPB_STAGE_POTRF) {
       double* stage[2] = {(double*)(p->ws + p->off_stage[0]), (double*)(p->ws + p->off_stage[1])};
@@ -411,7 +520,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       if (rc) return rc;
     }
     if (stages & GPB_STAGE_GRAD) {
-      CU(gpb::run_grad(dm, 1, p->n_max, p->n_hp_max, p->n_ops_max, p->dim, s), "grad");
+      CU(plan_grad(p, dm, s), "grad");
       int rc = dist_rc(gpb::run_grad_allreduce(p->h_desc0.grad, p->mats[0].n_hp + 1, *p->dist, s), "grad allreduce");
       if (rc) return rc;
     }
@@ -419,7 +528,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   }
   if (stages & GPB_STAGE_ASSEMBLE) {
     CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, (size_t)p->B * 4, s), "reset info");
-    CU(gpb::run_assemble_batched(dm, p->B, p->n_max, s), "assemble");
+    CU(plan_assemble(p, dm, s), "assemble");
   }
   // one large matrix, factorisation and inverse in the same call: the inverse of the block columns that are already
   // final runs under the factorisation's latency-bound tail (GPB_FUSE_TRTRI=0 keeps the stages apart)
@@ -441,7 +550,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     CU(gpb::run_alpha(dm, p->B, p->n_max, s), "alpha");
   }
   if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
-  if (stages & GPB_STAGE_GRAD) CU(gpb::run_grad(dm, p->B, p->n_max, p->n_hp_max, p->n_ops_max, p->dim, s), "grad");
+  if (stages & GPB_STAGE_GRAD) CU(plan_grad(p, dm, s), "grad");
   return 0;
 }
 

@@ -312,36 +312,6 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
   cp_async_wait<0>();
 }
 
-// Enumeration of the tiles of a lower-triangular region cut into (BM-row x BN-column) tiles, R = BN / BM:
-// column tile c (units of BN) owns the row tiles ti >= R*c (units of BM), ti < Tm.  Columns restricted to [c_lo, c_hi).
-__host__ __device__ inline long long tri_count(int Tm, int R, int c_lo, int c_hi) {
-  const int Tn = (Tm + R - 1) / R;   // column tiles that own at least one row tile
-  if (c_hi > Tn) c_hi = Tn;
-  if (c_hi <= c_lo) return 0;
-  const long long w = c_hi - c_lo, Tp = Tm - (long long)R * c_lo;
-  return w * Tp - (long long)R * w * (w - 1) / 2;
-}
-// 32-bit / single-precision fast path (every launch of the path: Tm <= 16384, so all counts fit in 31 bits): the
-// persistent kernel evaluates this twice per tile, so it must stay a few dozen instructions.
-__device__ __forceinline__ bool tri_map(unsigned idx, int Tm, int R, int c_lo, int c_hi, int& ti, int& tj) {
-  const int Tn = (Tm + R - 1) / R;
-  if (c_hi > Tn) c_hi = Tn;
-  if (c_hi <= c_lo) return false;
-  const int w = c_hi - c_lo, Tp = Tm - R * c_lo;
-  const int cnt = w * Tp - R * (w * (w - 1) / 2);
-  if (idx >= (unsigned)cnt) return false;
-  const float bq = (float)Tp + 0.5f * (float)R;
-  int c = (int)floorf((bq - sqrtf(fmaxf(bq * bq - 2.0f * (float)R * (float)idx, 0.0f))) / (float)R);
-  c = max(0, min(c, w - 1));
-  // prefix(c) = c * Tp - R * c (c - 1) / 2 tiles precede column c
-  while (c > 0 && c * Tp - R * (c * (c - 1) / 2) > (int)idx) --c;
-  while ((c + 1) * Tp - R * ((c + 1) * c / 2) <= (int)idx) ++c;
-  const int off = (int)idx - (c * Tp - R * (c * (c - 1) / 2));
-  tj = c + c_lo;
-  ti = R * tj + off;
-  return true;
-}
-
 // The same lower-triangular tile set in SUPER-TILE order: tile columns are taken in groups of G; inside a group the
 // row tiles run from the group's first diagonal tile to the bottom and the column index runs fastest.  Concurrently
 // running CTAs then cover ~(wave / G) row tiles x G column tiles instead of a whole column sweep, which cuts the distinct

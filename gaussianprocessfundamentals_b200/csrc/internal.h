@@ -40,11 +40,13 @@ int potrf_outer_blocks(int n_max);   // 128-blocks per outer panel of the factor
 cudaError_t linalg_init();
 
 // ---- assemble.cu ----------------------------------------------------------------------------------------------
-cudaError_t run_assemble_batched(const GpbMat* dmats, int B, int n_max, cudaStream_t s);
+cudaError_t run_assemble_batched(const GpbMat* dmats, const int* which, int B, int n_max, cudaStream_t s);
 cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int cp_mode, const double* X,
                               const double* X2, long long n, long long m, const double* hp_dev, int n_hp,
                               const double* noise_dev, double* K, long long ldk, int lower_only, cudaStream_t s);
-cudaError_t run_grad(const GpbMat* dmats, int B, int n_max, int n_hp_max, int n_ops_max, int dim, cudaStream_t s);
+cudaError_t run_grad_tiles(const GpbMat* dmats, const int* which, int B, int n_max, int n_hp_max, int n_ops_max, int dim,
+                           cudaStream_t s);
+cudaError_t run_grad_reduce(const GpbMat* dmats, int B, int n_hp_max, cudaStream_t s);
 int grad_tiles(int n);
 cudaError_t assemble_init();
 

@@ -11,6 +11,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include "gpb_math.h"   // gpb_sincos / gpb_sin: no large-argument slow path (no local memory)
 
 #if defined(__CUDACC__)
 #define GPB_HD __host__ __device__ __forceinline__
@@ -38,11 +39,11 @@ enum GpbOp : int32_t {
 enum GpbCpMode : int32_t { GPB_CP_SIGMOID = 0, GPB_CP_INDICATOR = 1, GPB_CP_APPROX_INDICATOR = 2 };
 
 #define GPB_OP_WORDS 4
-#define GPB_MAX_OPS 96
+#define GPB_MAX_OPS 256
 #define GPB_MAX_STACK 8
 #define GPB_MAX_TAPE 64
 #define GPB_MAX_DIM 16
-#define GPB_MAX_HP 96
+#define GPB_MAX_HP 128
 
 struct GpbPair {
   const double* xi;  // [dim]
@@ -131,7 +132,7 @@ GPB_HD double gpb_leaf(int op, int a, int flags, const GpbPair& p, double* dk) {
       // would be amplified into the entry (the reference computes pi * (D / p), BaseKernels.py:447)
       const double u = M_PI * (D / h[1]);
       double s, c;
-      if (dk) sincos(u, &s, &c); else { s = sin(u); c = 0.0; }
+      if (dk) gpb_sincos(u, &s, &c); else { s = gpb_sin(u); c = 0.0; }
       const double sine = s * s;
       const double il2 = il * il;
       k0 = exp((-2.0 * sine) * il2);

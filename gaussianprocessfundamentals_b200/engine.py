@@ -62,9 +62,43 @@ class DeviceProgram:
             cls._cache[key] = prog
         return prog
 
+    @classmethod
+    def get_many(cls, specs: Sequence, dim: int, scaled: bool, cp_mode: int) -> List["DeviceProgram"]:
+        """One program per spec; programs that do not exist yet are created on a thread pool: gpb_program_create compiles
+        the kernels specialised for the program with NVRTC (0.4 - 1.5 s each) and releases the GIL while it does."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        compiled = [compile_spec(spec, dim, scaled) for spec in specs]
+        dev = torch.cuda.current_device()
+        keys = [(c.signature(), int(cp_mode), dev) for c in compiled]
+        missing = {}
+        for k, c in zip(keys, compiled):
+            if k not in cls._cache and k not in missing:
+                missing[k] = c
+        if len(missing) > 1:
+            def make(c):
+                torch.cuda.set_device(dev)
+                return cls(c, cp_mode)
+            with ThreadPoolExecutor(max_workers=min(len(missing), os.cpu_count() or 4, 32)) as pool:
+                for k, prog in zip(missing, pool.map(make, missing.values())):
+                    cls._cache[k] = prog
+        elif missing:
+            (k, c), = missing.items()
+            cls._cache[k] = cls(c, cp_mode)
+        return [cls._cache[k] for k in keys]
+
     @property
     def n_hp(self) -> int:
         return self.compiled.n_hp
+
+    @property
+    def specialised(self) -> bool:
+        """the program runs on kernels generated and compiled for it (csrc/jit.cu), not on the interpreter"""
+        return bool(_lib.load().gpb_program_is_specialised(self.handle))
+
+    @property
+    def jit_note(self) -> str:
+        return _lib.load().gpb_program_jit_note(self.handle).decode("utf-8", "replace")
 
     def __del__(self):
         try:

@@ -14,7 +14,7 @@ from typing import List, Tuple
 import numpy as np
 
 OP = {"SE": 1, "PER": 2, "LIN": 3, "MAT32": 4, "MAT52": 5, "WN": 6, "SE_ARD": 7, "L2": 8, "L1": 9, "ADD2": 16, "MUL2": 17, "CPW": 18}
-MAX_OPS, MAX_STACK, MAX_TAPE, MAX_DIM, MAX_HP = 96, 8, 64, 16, 96
+MAX_OPS, MAX_STACK, MAX_TAPE, MAX_DIM, MAX_HP = 256, 8, 64, 16, 128
 
 
 def leaf_entries(kind: str, dim: int, scaled: bool) -> List[int]:
@@ -33,7 +33,8 @@ def leaf_entries(kind: str, dim: int, scaled: bool) -> List[int]:
 
 
 class CompiledProgram:
-    def __init__(self, code: np.ndarray, entries: List[Tuple[int, int]], n_hp: int, dim: int, scaled: bool):
+    def __init__(self, code: np.ndarray, entries: List[Tuple[int, int]], n_hp: int, dim: int, scaled: bool, tape: int = 0):
+        self.tape = tape            # entries the interpreter's gradient tape would need (MAX_TAPE: interpreter only)
         self.code = code            # int32 [n_ops, 4]
         self.entries = entries      # (offset, size) of each hp list entry in the flat vector
         self.n_hp = n_hp
@@ -106,13 +107,14 @@ def compile_spec(spec, dim: int, scaled: bool = False) -> CompiledProgram:
         raise ValueError("kernel tree too large: %d ops > %d" % (len(ops), MAX_OPS))
     if state["max_sp"] > MAX_STACK:
         raise ValueError("kernel tree too deep: stack %d > %d" % (state["max_sp"], MAX_STACK))
-    if state["tape"] > MAX_TAPE:
-        raise ValueError("kernel tree needs a gradient tape of %d > %d" % (state["tape"], MAX_TAPE))
+    # MAX_TAPE limits the INTERPRETER's gradient sweep only: kernels specialised per program (csrc/jit.cu) have no tape,
+    # so the limit is enforced by gpb_program_create, which knows whether the run-time compiler is available
     if state["off"] > MAX_HP:
         raise ValueError("too many hyper-parameters: %d > %d" % (state["off"], MAX_HP))
     if dim > MAX_DIM:
         raise ValueError("input dimensionality %d > %d" % (dim, MAX_DIM))
-    return CompiledProgram(np.asarray(ops, dtype=np.int32).reshape(-1, 4), entries, state["off"], dim, scaled)
+    return CompiledProgram(np.asarray(ops, dtype=np.int32).reshape(-1, 4), entries, state["off"], dim, scaled,
+                           tape=state["tape"])
 
 
 def flatten_hp(entries: List[Tuple[int, int]], hp_list, n_hp: int) -> np.ndarray:

@@ -78,6 +78,21 @@ long long gpb_launch_count(void);
  * cp_mode: 0 sigmoid, 1 indicator, 2 approx-indicator (global_parameters.py:10-13,44).                       */
 int gpb_program_create(const int32_t* code, int n_ops, int dim, int cp_mode, gpb_program_t** out);
 int gpb_program_num_hp(const gpb_program_t* prog);
+/* Run-time specialisation.  gpb_program_create also turns the program into straight-line CUDA (all stack / tape /
+ * adjoint slots of the interpreter become registers), compiles it with NVRTC for the device in use and uses those
+ * kernels for the assembly and trace-gradient stages of every plan the program is part of; GPs of a plan that share a
+ * program are one launch.  Without NVRTC (or with GPB_JIT=0) the interpreter kernels run instead - same results to
+ * rounding - and programs whose gradient tape exceeds the interpreter's 64 entries are refused.
+ *   gpb_program_is_specialised : 1 when the program runs on its own kernels
+ *   gpb_jit_source / gpb_jit_cubin : host-only (no GPU): the generated source / its CUBIN for `arch` ("sm_100a"), for
+ *                                    inspection and tests; `needed` receives the size, buf may be NULL            */
+int gpb_program_is_specialised(const gpb_program_t* prog);
+const char* gpb_program_jit_note(const gpb_program_t* prog);
+int gpb_jit_available(void);
+int gpb_jit_set_nvrtc_path(const char* path);
+int gpb_jit_source(const int32_t* code, int n_ops, int dim, int cp_mode, char* buf, size_t capacity, size_t* needed);
+int gpb_jit_cubin(const int32_t* code, int n_ops, int dim, int cp_mode, const char* arch, void* buf, size_t capacity,
+                  size_t* needed);
 void gpb_program_destroy(gpb_program_t* prog);
 
 /* ---- covariance assembly ----------------------------------------------------------------------------------

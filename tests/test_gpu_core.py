@@ -328,3 +328,78 @@ print("ok")
     env = dict(os.environ, GPB_POTRF_KB="2")
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+# ---- kernels specialised per program (csrc/jit.cu) vs the interpreter kernels ---------------------------------------------
+def test_programs_run_on_specialised_kernels():
+    """every program of this file is compiled to its own assembly / gradient kernels (NVRTC); the interpreter is the
+    fallback only"""
+    eng = _eng()
+    from gaussianprocessfundamentals_b200 import _lib
+    assert _lib.load().gpb_jit_available() == 1
+    for name, (tree, hp) in TREES.items():
+        prog = eng.DeviceProgram.get(tree, 1, False, 1)
+        assert prog.specialised, (name, prog.jit_note)
+
+
+def test_c3_grammar_worst_case_tree_evaluates():
+    """depth-3, 3-ary MUL of PER leaves (27 leaves, 54 hyper-parameters, interpreter tape 106 > 64): accepted and correct
+    on the specialised kernels"""
+    eng = _eng()
+    tree = ("MUL", [("MUL", [("MUL", [("PER",)] * 3)] * 3)] * 3)
+    rng = np.random.default_rng(11)
+    hp = []
+    for _ in range(27):
+        hp += [float(rng.uniform(2.0, 4.0)), float(rng.uniform(0.3, 0.9))]     # long length scales: the product stays O(1)
+    n = 300
+    plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, n)
+    assert info[0] == 0
+    ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, reference_distance=False)
+    assert abs(nll[0] - ref) <= LL_RTOL * abs(ref)
+    gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+    assert np.max(np.abs(grads[0] - gflat)) <= GRAD_RTOL * np.max(np.abs(gflat))
+
+
+def test_interpreter_kernels_subprocess():
+    """GPB_JIT=0 (read once per process) keeps every program on the interpreter kernels - the path of a host without
+    NVRTC: the oracle parity tests of this file must hold there too, and the two paths must agree to rounding"""
+    import subprocess
+    import sys
+    script = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from gaussianprocessfundamentals_b200 import engine as eng, _lib
+from oracle import gp_oracle as orc
+from tests.test_gpu_core import TREES, _run_plan, _flat
+assert _lib.load().gpb_jit_available() == 0
+out = {}
+for name, (tree, hp) in TREES.items():
+    for n in (129, 700):
+        plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, n, host=(n == 700))
+        assert not eng.DeviceProgram.get(tree, 1, False, 1).specialised
+        ref, gref, gnoise = orc.nll_and_grad(tree, hp, 1e-2, x, y, reference_distance=False)
+        assert info[0] == 0 and abs(nll[0] - ref) <= 1e-10 * abs(ref), (name, n, nll[0], ref)
+        gflat = np.concatenate([np.asarray(g).reshape(-1) for g in gref] + [[gnoise]])
+        assert np.max(np.abs(grads[0] - gflat)) <= 1e-8 * np.max(np.abs(gflat)), (name, n)
+        print("R", name, n, repr(float(nll[0])), " ".join(repr(float(v)) for v in grads[0]))
+# a tree beyond the interpreter's tape is refused with a clear message
+try:
+    eng.DeviceProgram.get(("MUL", [("MUL", [("MUL", [("PER",)] * 3)] * 3)] * 3), 1, False, 1)
+    print("NOT REFUSED")
+except _lib.GpbError as exc:
+    assert "tape" in str(exc)
+print("ok")
+""" % ROOT
+    env = dict(os.environ, GPB_JIT="0")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "ok" in out.stdout and "NOT REFUSED" not in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    eng = _eng()
+    for line in out.stdout.splitlines():
+        if not line.startswith("R "):
+            continue
+        _, name, n, nll_i, *g_i = line.split()
+        tree, hp = TREES[name]
+        plan, x, y, nll, grads, info = _run_plan(eng, tree, hp, int(n), host=(int(n) == 700))
+        assert abs(nll[0] - float(nll_i)) <= 1e-12 * abs(nll[0]), (name, n)
+        gi = np.array([float(v) for v in g_i])
+        assert np.max(np.abs(grads[0] - gi)) <= 1e-10 * np.max(np.abs(gi)), (name, n)

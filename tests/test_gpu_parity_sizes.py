@@ -87,7 +87,8 @@ def test_c3_heterogeneous_candidates_match_oracle():
     order = sorted(range(256), key=lambda b: -len(hps[b]))[:B]
     x, _ = bench.make_xy(n, 2)
     ys = [bench.make_xy(n, 1000 + b)[1] for b in order]
-    progs = [eng.DeviceProgram.get(trees[b], 1, False, 1) for b in order]
+    progs = eng.DeviceProgram.get_many([trees[b] for b in order], 1, False, 1)
+    assert all(p.specialised for p in progs), [p.jit_note for p in progs if not p.specialised]
     plan = eng.Plan(progs, [n] * B, want_grad=True)
     nll, grads, info = plan.eval_host([hps[b] for b in order], [1e-2] * B, [x] * B, [y.reshape(-1) for y in ys])
     assert int(np.max(info)) == 0
