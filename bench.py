@@ -611,7 +611,7 @@ def run_batch(ctx, key, steps, warmup, cpu_leg):
 def _brief(rec):
     """sub-record: the numbers of a workload without the boilerplate of a full line"""
     keep = ("value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "stages_ms", "cholesky", "check",
-            "cpu_baseline", "n_gpus", "steps")
+            "cpu_baseline", "n_gpus", "steps", "specialised_kernels")
     out = {k: rec[k] for k in keep if k in rec}
     out["roofline_frac"] = rec["roofline"]["frac"]
     return out
