@@ -59,6 +59,7 @@ SIGNATURES = {
     "gpb_dist_panel_segments": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_int_p]),
     "gpb_trtri_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, c_int_p,
                                           ctypes.c_int]),
+    "gpb_debug_diag_clocks": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "gpb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 

@@ -762,6 +762,8 @@ int gpb_gemm(int a_kmajor, int b_kmajor, const double* A, int lda, const double*
   return 0;
 }
 
+int gpb_debug_diag_clocks(long long* out8) { return gpb::debug_diag_clocks(out8); }
+
 int gpb_microbench(int kind, int iters, int blocks, void* stream) {
   CU(gpb::run_microbench(kind, iters, blocks, (cudaStream_t)stream), "gpb_microbench");
   return 0;

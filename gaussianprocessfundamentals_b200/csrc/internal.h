@@ -38,6 +38,7 @@ cudaError_t run_microbench(int kind, int iters, int blocks, cudaStream_t s);
 int trtri_schedule_host(int n, const long long* fc, int n_fc, int* out, int cap);   // host-only: the overlapped inverse's schedule
 int potrf_outer_blocks(int n_max);   // 128-blocks per outer panel of the factorisation (1 or 2; GPB_POTRF_KB)
 cudaError_t linalg_init();
+int debug_diag_clocks(long long* out);   // developer builds (-DGPB_DIAG_CLOCKS=1): phase clocks of the last diagonal-block launch
 
 // ---- assemble.cu ----------------------------------------------------------------------------------------------
 cudaError_t run_assemble_batched(const GpbMat* dmats, const int* which, int B, int n_max, cudaStream_t s);

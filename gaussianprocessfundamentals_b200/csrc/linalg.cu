@@ -390,13 +390,290 @@ __global__ void __launch_bounds__(32 * NW, 1) diag_kernel_t(const GpbMat* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// diagonal block, second design (default): Cholesky in registers + in-place triangular inverse in one shared square.
+//
+// The [A; I] elimination above is bound by the LATENCY of its instruction stream (8 warps, 36 instructions per DMMA, a
+// pivot chain of shuffles).  This version cuts the work and the instruction count:
+//   * Only A is eliminated: the 136 lower 8 x 8 tiles live in registers as NEGATED accumulators (N = -C, so the rank-8
+//     update is N += P_i P_j^T with unmodified operands), 17 per warp, sorted by column.  A tile is never read again once
+//     its column has been published, so "dead" tiles need no predication - whole groups of four are skipped instead.
+//   * The 8 x 8 diagonal micro-block is factorised IN-THREAD by every thread that owns a row (36 broadcast loads, then
+//     straight-line rsqrt / mul / fma in registers: no shuffles, no barriers inside the pivot chain), and the same
+//     eliminations are applied to the thread's own row.
+//   * L accumulates in a 128 x 132 shared square (pitch = 4 mod 16: every DMMA fragment load - row- or k-major - is bank
+//     conflict free).  W = inv(L) is then computed IN PLACE by recursive doubling (8 -> 16 -> 32 -> 64 -> 128), all DMMA:
+//     T = L21 W11 goes to the (free) upper-right block of each sub-problem, W21 = -W22 T overwrites L21.
+// Rows of the carried right-hand side inside the block are ordinary non-pivot rows, exactly as above.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int D2_P = GPB_NB + 4;
+constexpr int D2_SMEM_BYTES = (GPB_NB * D2_P + GPB_NB + 8) * (int)sizeof(double);
+
+__host__ __device__ constexpr int d2_prefix(int tj) { return tj * 16 - tj * (tj - 1) / 2; }   // tiles left of column tj
+
+// tile L = 8 * slot + warp of the column-sorted lower-triangular tile list (column tj holds ti = tj .. 15)
+__device__ __forceinline__ void d2_tile_of(int slot, int warp, int& ti, int& tj) {
+  const int L = 8 * slot + warp;
+  int c = 0;
+#pragma unroll
+  for (int q = 1; q < 16; ++q) c += (L >= d2_prefix(q)) ? 1 : 0;
+  tj = c;
+  ti = c + (L - d2_prefix(c));
+}
+
+// one 8 x 8 tile product on the shared square: acc += A(ra.., ka..) * B, fragments as in dmma884
+//   a: element (row, k) at S[(ka + k) * P + ra + row]      b: element (k, col) at S[bk + k * bstride_k + col * bstride_c]
+__device__ __forceinline__ void d2_mma8(double (&acc)[2], const double* __restrict__ S, int ra, int ka, int boff, int bsk,
+                                        int bsc, int lr, int lk) {
+  const double a0 = S[(ka + lk) * D2_P + ra + lr], a1 = S[(ka + 4 + lk) * D2_P + ra + lr];
+  const double b0 = S[boff + lk * bsk + lr * bsc], b1 = S[boff + (4 + lk) * bsk + lr * bsc];
+  dmma884(acc[0], acc[1], a0, b0);
+  dmma884(acc[0], acc[1], a1, b1);
+}
+
+// phase clocks of one diag2 launch (developer builds only: GPB_NVCC_EXTRA=-DGPB_DIAG_CLOCKS=1; read with
+// gpb_debug_diag_clocks): [0] load, [1] sum of panel phases, [2] sum of update phases, [3] log-det / identity rows,
+// [4] level 0 of the inverse, [5] levels 8 .. 64, [6] store
+#ifdef GPB_DIAG_CLOCKS
+__device__ long long g_diag_clocks[8];
+#define D2_CLK(slot) do { if (tid == 0) { const long long now_ = clock64(); g_diag_clocks[slot] += now_ - clk_; clk_ = now_; } } while (0)
+#else
+#define D2_CLK(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict__ mats, int k) {
+  extern __shared__ __align__(16) double dsm[];
+  double* S = dsm;                       // [128][D2_P] column-major square: L (lower) -> W = inv(L) (lower)
+  double* piv = S + GPB_NB * D2_P;       // [128] pivots L_jj
+  __shared__ int s_info;
+  const GpbMat d = mats[blockIdx.x];
+  const int nrows = d.n + d.aug;
+  const int r0 = k * GPB_NB;
+  if (r0 >= d.n) return;
+  const int bs = min(GPB_NB, nrows - r0);  // rows / columns held by the block (pivots + carried)
+  const int bf = min(GPB_NB, d.n - r0);    // pivots
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  const size_t ld = d.ld;
+  double* Ag = d.A + r0 + (size_t)r0 * ld;
+  if (tid == 0) s_info = 0;
+  if (tid < GPB_NB) piv[tid] = 1.0;
+#ifdef GPB_DIAG_CLOCKS
+  long long clk_ = clock64();
+  if (tid == 0) for (int q = 0; q < 8; ++q) g_diag_clocks[q] = 0;
+#endif
+
+  // ---- the lower triangle as negated accumulator tiles ---------------------------------------------------------------
+  constexpr int NS = 17;
+  double acc[NS][2];
+  int pos[NS];                            // (ti * 8 + lr) | (tj * 8 + lr) << 8 | tj << 16
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    int ti, tj;
+    d2_tile_of(s, warp, ti, tj);
+    pos[s] = (ti * 8 + lr) | ((tj * 8 + lr) << 8) | (tj << 16);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int row = ti * 8 + lr, col = tj * 8 + 2 * lk + e;
+      acc[s][e] = (row < bs && col < bs && row >= col) ? -Ag[row + (size_t)col * ld] : 0.0;
+    }
+    if (tj == 0) {                        // publish panel column 0
+      S[(2 * lk) * D2_P + ti * 8 + lr] = -acc[s][0];
+      S[(2 * lk + 1) * D2_P + ti * 8 + lr] = -acc[s][1];
+    }
+  }
+  __syncthreads();
+  D2_CLK(0);
+
+  const int R = tid;                       // row owned in the panel phase (threads 0 .. 127)
+  const int nsteps = (bs + 7) / 8;
+  for (int m = 0; m < nsteps; ++m) {
+    const int c0 = 8 * m;
+    // ---- (1) panel: in-thread factorisation of the 8 x 8 micro-block, same eliminations on the own row --------------
+    if (R < GPB_NB && R >= c0) {
+      double D[8][8], a[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        a[c] = S[(c0 + c) * D2_P + R];
+#pragma unroll
+        for (int i = c; i < 8; ++i) D[i][c] = S[(c0 + c) * D2_P + c0 + i];      // broadcast loads (same address per warp)
+      }
+      const int npiv = min(8, max(0, bf - c0));
+      const int rl = R - c0;               // < 8: this row lies inside the micro-block
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < npiv) {                    // uniform
+          const double dv = D[c][c];
+          // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_cc = d * rsqrt(d)
+          const double inv = rsqrt(dv);
+          if (R == c0 && !(dv > 0.0) && s_info == 0) s_info = r0 + c0 + c + 1;
+          if (rl == c) piv[c0 + c] = dv * inv;
+#pragma unroll
+          for (int i = c + 1; i < 8; ++i) D[i][c] *= inv;
+          const double xc = a[c] * inv;
+#pragma unroll
+          for (int j = c + 1; j < 8; ++j) {
+#pragma unroll
+            for (int i = j; i < 8; ++i) D[i][j] = fma(-D[i][c], D[j][c], D[i][j]);
+            a[j] = fma(-xc, D[j][c], a[j]);
+          }
+          a[c] = xc;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        // rows of the micro-block itself: explicit zeros above the diagonal (those entries were never loaded)
+        const double v = (rl < c) ? 0.0 : a[c];
+        S[(c0 + c) * D2_P + R] = v;
+        if (R < bs && c0 + c < bs) Ag[R + (size_t)(c0 + c) * ld] = v;
+      }
+    }
+    __syncthreads();
+    D2_CLK(1);
+    // ---- (2) rank-8 update of the live tiles (groups of four: dead tiles are a prefix and are never read again) -------
+    if (m + 1 < nsteps) {
+#pragma unroll
+      for (int g0 = 0; g0 < NS; g0 += 4) {
+        constexpr int G = 4;
+        const int last = (g0 + G - 1 < NS) ? g0 + G - 1 : NS - 1;
+        if ((pos[last] >> 16) > m) {       // uniform per warp: the group has at least one live tile
+          double a0[G], a1[G], b0[G], b1[G];
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            if (g0 + u < NS) {
+              const int ra = pos[g0 + u] & 255, rb = (pos[g0 + u] >> 8) & 255;
+              a0[u] = S[(c0 + lk) * D2_P + ra]; a1[u] = S[(c0 + 4 + lk) * D2_P + ra];
+              b0[u] = S[(c0 + lk) * D2_P + rb]; b1[u] = S[(c0 + 4 + lk) * D2_P + rb];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < G; ++u)
+            if (g0 + u < NS) dmma884(acc[g0 + u][0], acc[g0 + u][1], a0[u], b0[u]);
+#pragma unroll
+          for (int u = 0; u < G; ++u)
+            if (g0 + u < NS) dmma884(acc[g0 + u][0], acc[g0 + u][1], a1[u], b1[u]);
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            if (g0 + u < NS && (pos[g0 + u] >> 16) == m + 1) {     // next panel column: publish
+              const int ra = pos[g0 + u] & 255;
+              S[(c0 + 8 + 2 * lk) * D2_P + ra] = -acc[g0 + u][0];
+              S[(c0 + 8 + 2 * lk + 1) * D2_P + ra] = -acc[g0 + u][1];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    D2_CLK(2);
+  }
+
+  // ---- log-det partial, info -------------------------------------------------------------------------------------------
+  if (warp < 4) {
+    double lsum = (tid < bf) ? log(piv[tid]) : 0.0;
+    lsum = warp_sum(lsum);
+    if (lane == 0) piv[GPB_NB + warp] = lsum;
+  }
+  // ---- W = inv(L) in place.  Rows / columns that hold no pivot (a partial last block, the carried row) become identity
+  //      rows so that nothing non-finite can leak into the pivot rows through 0 * x products.
+  if (bf < GPB_NB) {
+    for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+      const int i = idx & (GPB_NB - 1), j = idx >> 7;
+      if (i >= bf || j >= bf) S[j * D2_P + i] = (i == j) ? 1.0 : 0.0;   // also the never-initialised part of the square
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    d.part[k] = (piv[GPB_NB] + piv[GPB_NB + 1]) + (piv[GPB_NB + 2] + piv[GPB_NB + 3]);
+    if (s_info != 0 && *d.info == 0) *d.info = s_info;
+  }
+  D2_CLK(3);
+  // level 0: the sixteen 8 x 8 diagonal micro-blocks, one thread each (lanes 0, 1 of every warp), in registers
+  if (lane < 2) {
+    const int b0 = (warp * 2 + lane) * 8;
+    double Lm[8][8], Wm[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int i = c; i < 8; ++i) Lm[i][c] = S[(b0 + c) * D2_P + b0 + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      Wm[j][j] = 1.0 / Lm[j][j];
+#pragma unroll
+      for (int i = j + 1; i < 8; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = j; q < i; ++q) t = fma(Lm[i][q], Wm[q][j], t);
+        Wm[i][j] = -t / Lm[i][i];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int i = c; i < 8; ++i) S[(b0 + c) * D2_P + b0 + i] = Wm[i][c];
+  }
+  __syncthreads();
+  D2_CLK(4);
+  // levels s = 8 .. 64: [W11 0; L21 W22] -> W21 = -W22 (L21 W11)
+  for (int s = 8; s < GPB_NB; s *= 2) {
+    const int ts = s / 8;                  // tiles per side of a sub-problem
+    const int ntiles = (GPB_NB / (2 * s)) * ts * ts;
+    // phase T: T = L21 W11 into the upper-right block (rows r0.., columns rA..), k >= tile column (W11 lower triangular)
+    for (int t = warp; t < ntiles; t += 8) {
+      const int p = t / (ts * ts), rem = t - p * ts * ts;
+      const int tj = rem / ts, ti = (rem + tj) % ts;          // rotate rows per column: spreads the long k-ranges over warps
+      const int q0 = 2 * s * p, qA = q0 + s;
+      double c2[2] = {0.0, 0.0};
+      for (int kk = tj; kk < ts; ++kk)
+        d2_mma8(c2, S, qA + ti * 8, q0 + kk * 8, (q0 + tj * 8) * D2_P + q0 + kk * 8, 1, D2_P, lr, lk);
+      S[(qA + tj * 8 + 2 * lk) * D2_P + q0 + ti * 8 + lr] = c2[0];
+      S[(qA + tj * 8 + 2 * lk + 1) * D2_P + q0 + ti * 8 + lr] = c2[1];
+    }
+    __syncthreads();
+    // phase W: W21 = -W22 T, k <= tile row (W22 lower triangular)
+    for (int t = warp; t < ntiles; t += 8) {
+      const int p = t / (ts * ts), rem = t - p * ts * ts;
+      const int tj = rem / ts, ti = ts - 1 - ((rem + tj) % ts);
+      const int q0 = 2 * s * p, qA = q0 + s;
+      double c2[2] = {0.0, 0.0};
+      for (int kk = 0; kk <= ti; ++kk)
+        d2_mma8(c2, S, qA + ti * 8, qA + kk * 8, (qA + tj * 8) * D2_P + q0 + kk * 8, 1, D2_P, lr, lk);
+      S[(q0 + tj * 8 + 2 * lk) * D2_P + qA + ti * 8 + lr] = -c2[0];
+      S[(q0 + tj * 8 + 2 * lk + 1) * D2_P + qA + ti * 8 + lr] = -c2[1];
+    }
+    __syncthreads();
+  }
+  D2_CLK(5);
+  double* Wg = d.Wd + (size_t)k * GPB_NB * GPB_NB;
+  for (int idx = tid; idx < GPB_NB * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), j = idx >> 7;
+    Wg[idx] = (i >= j && i < bf) ? S[j * D2_P + i] : 0.0;
+  }
+  D2_CLK(6);
+}
+
+int debug_diag_clocks(long long* out) {
+#ifdef GPB_DIAG_CLOCKS
+  return cudaMemcpyFromSymbol(out, g_diag_clocks, 8 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+#else
+  (void)out;
+  return -1;
+#endif
+}
+
+static int diag_design() {      // GPB_DIAG=old: the [A; I] elimination kernel
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_DIAG"); v = (e && e[0] == 'o') ? 0 : 1; }
+  return v;
+}
+
 static int diag_warps() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPB_DIAG_WARPS"); v = (e && atoi(e) == 16) ? 16 : 8; }
   return v;
 }
 static void launch_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
-  if (diag_warps() == 16) diag_kernel_t<16><<<B, 512, D_SMEM_BYTES, s>>>(dm, k);
+  if (diag_design() == 1) diag2_kernel<<<B, 256, D2_SMEM_BYTES, s>>>(dm, k);
+  else if (diag_warps() == 16) diag_kernel_t<16><<<B, 512, D_SMEM_BYTES, s>>>(dm, k);
   else diag_kernel_t<8><<<B, 256, D_SMEM_BYTES, s>>>(dm, k);
 }
 
@@ -582,6 +859,7 @@ cudaError_t linalg_init() {
   GPB_CK(set_smem_all<CfgHalf>());
   GPB_CK((set_smem<CfgQuarter, false, false, GeoSyrk>()));
   GPB_CK((set_smem<CfgQuarter, false, false, GeoPanel>()));
+  GPB_CK(cudaFuncSetAttribute(diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
   GPB_CK(cudaFuncSetAttribute(diag_kernel_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
   GPB_CK(cudaFuncSetAttribute(diag_kernel_t<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
   return cudaSuccess;

@@ -190,6 +190,8 @@ int gpb_trtri_schedule(int n, const long long* final_cols, int n_steps, int* tas
  * instruction), kind 1 = DFMA (64 flop per warp instruction); every thread issues 8 (kind 0) / 16 (kind 1)
  * independent instructions per iteration; `blocks` CTAs of 256 threads.                                         */
 int gpb_microbench(int kind, int iters, int blocks, void* stream);
+/* Developer builds only (-DGPB_DIAG_CLOCKS=1): SM clock counts of the phases of the last diagonal-block launch; -1 otherwise. */
+int gpb_debug_diag_clocks(long long* out8);
 
 #ifdef __cplusplus
 }
