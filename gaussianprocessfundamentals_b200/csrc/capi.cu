@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler is attached
+
 #include "../../include/gpb.h"
 #include "dist.h"
 #include "internal.h"
@@ -16,6 +18,12 @@
 namespace gpb {
 std::atomic<long long> g_launches{0};
 }  // namespace gpb
+
+// one NVTX range per stage of an evaluation (host side: brackets the launches of the stage on the timeline)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_err;
 static int fail_arg(int k, const char* what) {
@@ -491,10 +499,12 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   if (p->dist) {
 
     if (stages & GPB_STAGE_ASSEMBLE) {
+      NvtxRange r("gpb:assemble");
       CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
       CU(plan_assemble(p, dm, s), "assemble");
     }
     if (stages & GPB_STAGE_POTRF) {
+      NvtxRange r("gpb:potrf(dist)");
       double* stage[2] = {(double*)(p->ws + p->off_stage[0]), (double*)(p->ws + p->off_stage[1])};
       cudaError_t e = gpb::run_potrf_dist(dm, p->h_desc0, *p->dist, stage, p->ex);
       if (e != cudaSuccess) {
@@ -511,15 +521,18 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       return fail_cuda(e, where);
     };
     if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
+      NvtxRange r("gpb:trtri(dist)");
       int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), s), "trtri_dist");
       if (rc) return rc;
       CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
     }
     if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) {
+      NvtxRange r("gpb:lauum(dist)");
       int rc = dist_rc(gpb::run_lauum_dist(dm, p->h_desc0, *p->dist, s), "lauum_dist");
       if (rc) return rc;
     }
     if (stages & GPB_STAGE_GRAD) {
+      NvtxRange r("gpb:grad(dist)");
       CU(plan_grad(p, dm, s), "grad");
       int rc = dist_rc(gpb::run_grad_allreduce(p->h_desc0.grad, p->mats[0].n_hp + 1, *p->dist, s), "grad allreduce");
       if (rc) return rc;
@@ -527,6 +540,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     return 0;
   }
   if (stages & GPB_STAGE_ASSEMBLE) {
+    NvtxRange r("gpb:assemble");
     CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, (size_t)p->B * 4, s), "reset info");
     CU(plan_assemble(p, dm, s), "assemble");
   }
@@ -538,19 +552,31 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     static int fuse_env = -1;
     if (fuse_env < 0) { const char* fe = getenv("GPB_FUSE_TRTRI"); fuse_env = (fe && fe[0] == '0') ? 0 : 1; }
     fused_trtri = lookahead && fuse_env && (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) != 0;
+    NvtxRange r(fused_trtri ? "gpb:potrf+trtri" : "gpb:potrf");
     CU(gpb::run_potrf(dm, p->B, p->n_max, 1, lookahead, fused_trtri, p->ex), "potrf");
   }
   if (stages & GPB_STAGE_NLL) {
+    NvtxRange r("gpb:nll");
     const double log2pi = std::log(M_PI * 2.0);
     CU(gpb::run_finalize(dm, p->B, log2pi, s), "finalize");
   }
-  if (stages & GPB_STAGE_BACKSOLVE) CU(gpb::run_trsv(dm, p->B, p->n_max, 1, s), "backsolve");
+  if (stages & GPB_STAGE_BACKSOLVE) {
+    NvtxRange r("gpb:backsolve");
+    CU(gpb::run_trsv(dm, p->B, p->n_max, 1, s), "backsolve");
+  }
   if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
+    NvtxRange r("gpb:trtri");
     if (!fused_trtri) CU(gpb::run_trtri(dm, p->B, p->n_max, s), "trtri");
     CU(gpb::run_alpha(dm, p->B, p->n_max, s), "alpha");
   }
-  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
-  if (stages & GPB_STAGE_GRAD) CU(plan_grad(p, dm, s), "grad");
+  if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) {
+    NvtxRange r("gpb:lauum");
+    CU(gpb::run_lauum(dm, p->B, p->n_max, s), "lauum");
+  }
+  if (stages & GPB_STAGE_GRAD) {
+    NvtxRange r("gpb:grad");
+    CU(plan_grad(p, dm, s), "grad");
+  }
   return 0;
 }
 
@@ -562,6 +588,7 @@ int gpb_plan_eval_host(gpb_plan_t* p, int stages, const double* const* X_host, c
   if (!hp_host && p->hp_prefix[p->B] > 0) return fail_arg(5, "hp_host is null");
   if (!noise_host) return fail_arg(6, "noise_host is null");
   cudaStream_t s = (cudaStream_t)stream;
+  NvtxRange r_host("gpb:eval_host");
   // Fewer, larger copies: when the caller's X / y buffers are laid out like the plan's data region (one staging buffer,
   // gpb_plan_input_layout) all inputs travel in ONE cudaMemcpyAsync instead of 2 B of them (1024 blocks: 2048 copies
   // cost a sixth of the evaluation).

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(32 * NW, 1) diag_kernel_t(const GpbMat* __rest
 // Rows of the carried right-hand side inside the block are ordinary non-pivot rows, exactly as above.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int D2_P = GPB_NB + 4;
-constexpr int D2_SMEM_BYTES = (GPB_NB * D2_P + GPB_NB + 8) * (int)sizeof(double);
+constexpr int D2_SMEM_BYTES = (GPB_NB * D2_P + 2 * GPB_NB + 8) * (int)sizeof(double);
 
 __host__ __device__ constexpr int d2_prefix(int tj) { return tj * 16 - tj * (tj - 1) / 2; }   // tiles left of column tj
 
@@ -441,10 +441,23 @@ __device__ long long g_diag_clocks[8];
 #define D2_CLK(slot) do { } while (0)
 #endif
 
+// 1 / sqrt(d) for the pivot chain: hardware seed (MUFU.RSQ64H, ~2^-20) and ONE third-order step
+//   e = 1 - d y^2,  y <- y + y e (1/2 + 3/8 e)      (error ~ 5/16 e^3 < 2^-60)
+// - four dependent FP64 operations behind the seed.  The library's rsqrt adds range checks for zero / subnormal / infinite
+// arguments; a non-positive pivot yields NaN here as there (the launch reports it through `info`).
+__device__ __forceinline__ double d2_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double u = y * e;
+  return fma(u, fma(e, 0.375, 0.5), y);
+}
+
 __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict__ mats, int k) {
   extern __shared__ __align__(16) double dsm[];
   double* S = dsm;                       // [128][D2_P] column-major square: L (lower) -> W = inv(L) (lower)
-  double* piv = S + GPB_NB * D2_P;       // [128] pivots L_jj
+  double* piv = S + GPB_NB * D2_P;       // [128] pivots L_jj, [128 .. 136) scratch, [136 .. 264) their reciprocals
   __shared__ int s_info;
   const GpbMat d = mats[blockIdx.x];
   const int nrows = d.n + d.aug;
@@ -457,7 +470,8 @@ __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict_
   const size_t ld = d.ld;
   double* Ag = d.A + r0 + (size_t)r0 * ld;
   if (tid == 0) s_info = 0;
-  if (tid < GPB_NB) piv[tid] = 1.0;
+  double* rpiv = piv + GPB_NB + 8;       // 1 / L_jj (the rsqrt of the pivot chain, <= 1 ulp)
+  if (tid < GPB_NB) { piv[tid] = 1.0; rpiv[tid] = 1.0; }
 #ifdef GPB_DIAG_CLOCKS
   long long clk_ = clock64();
   if (tid == 0) for (int q = 0; q < 8; ++q) g_diag_clocks[q] = 0;
@@ -500,14 +514,14 @@ __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict_
       }
       const int npiv = min(8, max(0, bf - c0));
       const int rl = R - c0;               // < 8: this row lies inside the micro-block
+      double dvs[8], invs[8];              // pivots and their inverse roots (bookkeeping after the chain, off its path)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
+        dvs[c] = 1.0; invs[c] = 1.0;
         if (c < npiv) {                    // uniform
           const double dv = D[c][c];
-          // 1/sqrt(d) by the hardware seed + Newton (rsqrt, <= 1 ulp), L_cc = d * rsqrt(d)
-          const double inv = rsqrt(dv);
-          if (R == c0 && !(dv > 0.0) && s_info == 0) s_info = r0 + c0 + c + 1;
-          if (rl == c) piv[c0 + c] = dv * inv;
+          const double inv = d2_rsqrt(dv);
+          dvs[c] = dv; invs[c] = inv;
 #pragma unroll
           for (int i = c + 1; i < 8; ++i) D[i][c] *= inv;
           const double xc = a[c] * inv;
@@ -518,6 +532,16 @@ __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict_
             a[j] = fma(-xc, D[j][c], a[j]);
           }
           a[c] = xc;
+        }
+      }
+      if (rl == 0) {                       // one thread per micro-block: pivots L_cc = d / sqrt(d), their reciprocals, info
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < npiv) {
+            piv[c0 + c] = dvs[c] * invs[c];
+            rpiv[c0 + c] = invs[c];
+            if (!(dvs[c] > 0.0) && s_info == 0) s_info = r0 + c0 + c + 1;
+          }
         }
       }
 #pragma unroll
@@ -587,58 +611,107 @@ __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict_
     if (s_info != 0 && *d.info == 0) *d.info = s_info;
   }
   D2_CLK(3);
-  // level 0: the sixteen 8 x 8 diagonal micro-blocks, one thread each (lanes 0, 1 of every warp), in registers
-  if (lane < 2) {
-    const int b0 = (warp * 2 + lane) * 8;
-    double Lm[8][8], Wm[8][8];
+  // level 0: the sixteen 8 x 8 diagonal micro-blocks; thread t < 128 owns column (t & 7) of block (t >> 3):
+  //   W_jj = 1 / L_jj,  W_ij = -(1 / L_ii) sum_{q = j}^{i-1} L_iq W_qj   (the columns of an inverse are independent)
+  if (tid < GPB_NB) {
+    const int b0 = (tid >> 3) * 8, j = tid & 7;
+    double Wc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int i = 0; i < 8; ++i) {
+      double t = 0.0;
 #pragma unroll
-      for (int i = c; i < 8; ++i) Lm[i][c] = S[(b0 + c) * D2_P + b0 + i];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      Wm[j][j] = 1.0 / Lm[j][j];
-#pragma unroll
-      for (int i = j + 1; i < 8; ++i) {
-        double t = 0.0;
-#pragma unroll
-        for (int q = j; q < i; ++q) t = fma(Lm[i][q], Wm[q][j], t);
-        Wm[i][j] = -t / Lm[i][i];
-      }
+      for (int q = 0; q < i; ++q)
+        if (q >= j) t = fma(S[(b0 + q) * D2_P + b0 + i], Wc[q], t);
+      const double ri = (b0 + i < bf) ? rpiv[b0 + i] : 1.0;
+      Wc[i] = (i == j) ? ri : ((i > j) ? -t * ri : 0.0);
     }
+    __syncwarp();      // all loads of L precede the stores of W (lanes of a warp share micro-blocks)
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int i = c; i < 8; ++i) S[(b0 + c) * D2_P + b0 + i] = Wm[i][c];
+    for (int i = 0; i < 8; ++i)
+      if (i >= j) S[(b0 + j) * D2_P + b0 + i] = Wc[i];
   }
   __syncthreads();
   D2_CLK(4);
-  // levels s = 8 .. 64: [W11 0; L21 W22] -> W21 = -W22 (L21 W11)
-  for (int s = 8; s < GPB_NB; s *= 2) {
-    const int ts = s / 8;                  // tiles per side of a sub-problem
-    const int ntiles = (GPB_NB / (2 * s)) * ts * ts;
-    // phase T: T = L21 W11 into the upper-right block (rows r0.., columns rA..), k >= tile column (W11 lower triangular)
-    for (int t = warp; t < ntiles; t += 8) {
-      const int p = t / (ts * ts), rem = t - p * ts * ts;
-      const int tj = rem / ts, ti = (rem + tj) % ts;          // rotate rows per column: spreads the long k-ranges over warps
-      const int q0 = 2 * s * p, qA = q0 + s;
-      double c2[2] = {0.0, 0.0};
-      for (int kk = tj; kk < ts; ++kk)
-        d2_mma8(c2, S, qA + ti * 8, q0 + kk * 8, (q0 + tj * 8) * D2_P + q0 + kk * 8, 1, D2_P, lr, lk);
-      S[(qA + tj * 8 + 2 * lk) * D2_P + q0 + ti * 8 + lr] = c2[0];
-      S[(qA + tj * 8 + 2 * lk + 1) * D2_P + q0 + ti * 8 + lr] = c2[1];
+  // levels s = 8 .. 64: [W11 0; L21 W22] -> W21 = -W22 (L21 W11).  A warp computes a 2 x 2 block of 8 x 8 tiles at a time
+  // (four independent accumulator chains, every fragment load feeds two DMMAs); index math is shifts (s is a power of 2).
+  {
+    // s = 8: one tile per sub-problem and warp: W21 = -W22 * (L21 * W11) with all three factors 8 x 8
+    const int q0 = 16 * warp, qA = q0 + 8;
+    double c2[2] = {0.0, 0.0};
+    d2_mma8(c2, S, qA, q0, q0 * D2_P + q0, 1, D2_P, lr, lk);                      // T = L21 W11
+    S[(qA + 2 * lk) * D2_P + q0 + lr] = c2[0];
+    S[(qA + 2 * lk + 1) * D2_P + q0 + lr] = c2[1];
+    __syncwarp();
+    double w2[2] = {0.0, 0.0};
+    d2_mma8(w2, S, qA, qA, qA * D2_P + q0, 1, D2_P, lr, lk);                      // W22 T
+    S[(q0 + 2 * lk) * D2_P + qA + lr] = -w2[0];
+    S[(q0 + 2 * lk + 1) * D2_P + qA + lr] = -w2[1];
+  }
+  __syncthreads();
+  for (int ls = 4; ls < 7; ++ls) {          // s = 16, 32, 64
+    const int s = 1 << ls;
+    const int lb = ls - 4;                  // log2 of the 2 x 2 blocks per side of a sub-problem (s / 16)
+    const int nb = (GPB_NB >> (ls + 1)) << (2 * lb);   // sub-problems x blocks per sub-problem: 4, 8, 16
+    // phase T: T = L21 W11 into the upper-right block; k >= tile column (W11 lower triangular)
+    for (int t = warp; t < nb; t += 8) {
+      const int p = t >> (2 * lb), rem = t & ((1 << (2 * lb)) - 1);
+      const int bj = rem >> lb, bi = (rem + bj) & ((1 << lb) - 1);     // rotate rows per column: balances the k-ranges
+      const int q0 = p << (ls + 1), qA = q0 + s;
+      const int ti = 2 * bi, tj = 2 * bj, ts = s >> 3;
+      double c[2][2][2] = {};
+      for (int kk = tj; kk < ts; ++kk) {
+        const int ka = q0 + kk * 8;
+        const double a00 = S[(ka + lk) * D2_P + qA + ti * 8 + lr], a01 = S[(ka + 4 + lk) * D2_P + qA + ti * 8 + lr];
+        const double a10 = S[(ka + lk) * D2_P + qA + ti * 8 + 8 + lr], a11 = S[(ka + 4 + lk) * D2_P + qA + ti * 8 + 8 + lr];
+        const double* bp = S + (q0 + tj * 8 + lr) * D2_P + ka + lk;
+        const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * D2_P], b11 = bp[8 * D2_P + 4];
+        dmma884(c[0][0][0], c[0][0][1], a00, b00); dmma884(c[1][0][0], c[1][0][1], a10, b00);     // column tj: every kk >= tj
+        if (kk > tj) {                      // column tj + 1: the tile (kk = tj, tj + 1) of W11 lies above its diagonal
+          dmma884(c[0][1][0], c[0][1][1], a00, b10); dmma884(c[1][1][0], c[1][1][1], a10, b10);
+        }
+        dmma884(c[0][0][0], c[0][0][1], a01, b01); dmma884(c[1][0][0], c[1][0][1], a11, b01);
+        if (kk > tj) {
+          dmma884(c[0][1][0], c[0][1][1], a01, b11); dmma884(c[1][1][0], c[1][1][1], a11, b11);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          S[(qA + (tj + v) * 8 + 2 * lk) * D2_P + q0 + (ti + u) * 8 + lr] = c[u][v][0];
+          S[(qA + (tj + v) * 8 + 2 * lk + 1) * D2_P + q0 + (ti + u) * 8 + lr] = c[u][v][1];
+        }
     }
     __syncthreads();
-    // phase W: W21 = -W22 T, k <= tile row (W22 lower triangular)
-    for (int t = warp; t < ntiles; t += 8) {
-      const int p = t / (ts * ts), rem = t - p * ts * ts;
-      const int tj = rem / ts, ti = ts - 1 - ((rem + tj) % ts);
-      const int q0 = 2 * s * p, qA = q0 + s;
-      double c2[2] = {0.0, 0.0};
-      for (int kk = 0; kk <= ti; ++kk)
-        d2_mma8(c2, S, qA + ti * 8, qA + kk * 8, (qA + tj * 8) * D2_P + q0 + kk * 8, 1, D2_P, lr, lk);
-      S[(q0 + tj * 8 + 2 * lk) * D2_P + qA + ti * 8 + lr] = -c2[0];
-      S[(q0 + tj * 8 + 2 * lk + 1) * D2_P + qA + ti * 8 + lr] = -c2[1];
+    // phase W: W21 = -W22 T; k <= tile row (W22 lower triangular)
+    for (int t = warp; t < nb; t += 8) {
+      const int p = t >> (2 * lb), rem = t & ((1 << (2 * lb)) - 1);
+      const int bj = rem >> lb, bi = ((1 << lb) - 1) - ((rem + bj) & ((1 << lb) - 1));
+      const int q0 = p << (ls + 1), qA = q0 + s;
+      const int ti = 2 * bi, tj = 2 * bj;
+      double c[2][2][2] = {};
+      for (int kk = 0; kk <= ti + 1; ++kk) {
+        const int ka = qA + kk * 8;
+        const double a00 = S[(ka + lk) * D2_P + qA + ti * 8 + lr], a01 = S[(ka + 4 + lk) * D2_P + qA + ti * 8 + lr];
+        const double a10 = S[(ka + lk) * D2_P + qA + ti * 8 + 8 + lr], a11 = S[(ka + 4 + lk) * D2_P + qA + ti * 8 + 8 + lr];
+        const double* bp = S + (qA + tj * 8 + lr) * D2_P + q0 + kk * 8 + lk;
+        const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * D2_P], b11 = bp[8 * D2_P + 4];
+        if (kk <= ti) {                     // row ti: the tile (ti, kk = ti + 1) of W22 lies above its diagonal
+          dmma884(c[0][0][0], c[0][0][1], a00, b00); dmma884(c[0][1][0], c[0][1][1], a00, b10);
+        }
+        dmma884(c[1][0][0], c[1][0][1], a10, b00); dmma884(c[1][1][0], c[1][1][1], a10, b10);
+        if (kk <= ti) {
+          dmma884(c[0][0][0], c[0][0][1], a01, b01); dmma884(c[0][1][0], c[0][1][1], a01, b11);
+        }
+        dmma884(c[1][0][0], c[1][0][1], a11, b01); dmma884(c[1][1][0], c[1][1][1], a11, b11);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          S[(q0 + (tj + v) * 8 + 2 * lk) * D2_P + qA + (ti + u) * 8 + lr] = -c[u][v][0];
+          S[(q0 + (tj + v) * 8 + 2 * lk + 1) * D2_P + qA + (ti + u) * 8 + lr] = -c[u][v][1];
+        }
     }
     __syncthreads();
   }
@@ -874,13 +947,16 @@ static bool quarter_tiles() {
 // outer panel width of the factorisation in 128-blocks.  Measured on B200 (potrf, ms, kb = 1 / 2): n = 4096 3.16 / 3.43,
 // 8192 10.08 / 9.91, 16384 56.9 / 52.9, 32768 411 / 380 - the wider panel pays once the far update dominates.
 // GPB_POTRF_KB=1|2 overrides.
-static int kb_max(int n_max) {
+// Batches of independent GPs have no critical path to protect: the wider panel pays from n = 1024 on (C3 256 x n = 2048:
+// potrf 33.7 -> 32.1 ms, C4 1024 x n = 1024: 21.8 -> 21.1 ms).
+static int kb_max(int n_max, int B = 1) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("GPB_POTRF_KB");
     forced = e ? ((e[0] == '1') ? 1 : 2) : 0;
   }
   if (forced) return forced;
+  if (B >= 8) return n_max >= 1024 ? 2 : 1;
   return n_max >= 6144 ? 2 : 1;
 }
 
@@ -1075,7 +1151,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     GPB_CK(panel(k));
     int kb = 1;
     bool waited = false;
-    if (kb_max(n_max) > 1 && full_with_rows(k + 1)) {
+    if (kb_max(n_max, B) > 1 && full_with_rows(k + 1)) {
       // block column k+1 received its far update from the previous outer step on the side stream
       if (lookahead && step > 0) { GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(step - 1) & 1], 0)); waited = true; }
       GPB_CK(syrk(k, 1, 0, 1, ms, false));          // block column k+1 <- panel k (inside the 256-wide outer panel)

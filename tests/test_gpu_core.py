@@ -403,3 +403,31 @@ print("ok")
         assert abs(nll[0] - float(nll_i)) <= 1e-12 * abs(nll[0]), (name, n)
         gi = np.array([float(v) for v in g_i])
         assert np.max(np.abs(grads[0] - gi)) <= 1e-10 * np.max(np.abs(gi)), (name, n)
+
+
+def test_diagonal_block_factor_is_accurate_to_a_few_ulp():
+    """The pivot chain of the diagonal-block kernel uses its own 1/sqrt (hardware seed + one third-order step, csrc/linalg.cu
+    d2_rsqrt).  A sloppy seed would still pass the 1e-10 likelihood tolerance, so the factor itself is checked: the residual
+    K - L L^T of a 128 x 128 block, accumulated in extended precision, must stay within a few ulp of |K|."""
+    eng = _eng()
+    n = 128
+    x, y = _data(n)
+    tree, hp = TREES["composite"]
+    prog = eng.DeviceProgram.get(tree, 1, False, 1)
+    plan = eng.Plan([prog], [n], want_grad=True)
+    plan.set_data(0, torch.tensor(x), torch.tensor(y)); plan.set_hp(0, _flat(hp), 1e-2)
+    dev = torch.device("cuda")
+    K = eng.assemble(prog, torch.tensor(x, device=dev), None, torch.tensor(_flat(hp), device=dev),
+                     torch.tensor([1e-2], dtype=torch.float64, device=dev)).cpu().numpy()
+    plan.eval(eng.STAGES_LML)
+    L = torch.tril(plan.lower_matrix(0, eng.BUF_A)).cpu().numpy()
+    Lx = L.astype(np.longdouble)
+    resid = np.abs(K.astype(np.longdouble) - Lx @ Lx.T)
+    eps = np.finfo(np.float64).eps
+    assert float(resid.max()) <= 24 * eps * float(np.abs(K).max()), float(resid.max() / (eps * np.abs(K).max()))
+    # and the inverse of the block: W L = I to rounding (W = inv(L) from the recursive doubling inside the kernel)
+    plan.eval(eng.STAGE_INVERSE)
+    W = torch.tril(plan.lower_matrix(0, eng.BUF_A)).cpu().numpy().astype(np.longdouble)
+    ident = np.abs(W @ Lx - np.eye(n))
+    cond = float(np.abs(W).max() * np.abs(L).max())
+    assert float(ident.max()) <= 64 * eps * cond, (float(ident.max()), cond)
