@@ -470,6 +470,7 @@ def run_batch(ctx, key, steps, warmup, cpu_leg):
     plan.eval(eng.STAGES_LML_GRAD)
     torch.cuda.synchronize()
     launches_per_eval = eng.launch_count() - l0
+    nll_first = plan.results()[0].copy()      # compared bit for bit with the values after the timed region
 
     # ---- stage timings (one evaluation, CUDA events on the launching stream) -------------------------------------------
     stage_ms = {}
@@ -595,7 +596,8 @@ def run_batch(ctx, key, steps, warmup, cpu_leg):
         "cholesky": {"tflops": tf_potrf, "frac_of_fp64_tensor_peak": tf_potrf / peak,
                      "inverse_tflops": tf_inv, "inverse_frac": tf_inv / peak},
         "check": {"nll0": float(nll[0]), "info_max": int(np.max(info)),
-                  "e2e_matches_resident": bool(abs(nll_h[0] - nll[0]) <= 1e-12 * abs(nll[0]))},
+                  "e2e_matches_resident": bool(abs(nll_h[0] - nll[0]) <= 1e-12 * abs(nll[0])),
+                  "bitwise_reproducible": bool(np.array_equal(nll_first, nll))},
         # assembly and trace gradient run on kernels generated per kernel program and compiled at program creation
         # (csrc/jit.cu, NVRTC); set-up cost, outside the timed region like the plan construction
         "specialised_kernels": {"programs": len(set(id(p_) for p_ in progs)),

@@ -504,14 +504,21 @@ __global__ void __launch_bounds__(256, 1) diag2_kernel(const GpbMat* __restrict_
   for (int m = 0; m < nsteps; ++m) {
     const int c0 = 8 * m;
     // ---- (1) panel: in-thread factorisation of the 8 x 8 micro-block, same eliminations on the own row --------------
-    if (R < GPB_NB && R >= c0) {
-      double D[8][8], a[8];
+    const bool panel_thread = R < GPB_NB && R >= c0;
+    double D[8][8], a[8];
+    if (panel_thread) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         a[c] = S[(c0 + c) * D2_P + R];
 #pragma unroll
         for (int i = c; i < 8; ++i) D[i][c] = S[(c0 + c) * D2_P + c0 + i];      // broadcast loads (same address per warp)
       }
+    }
+    // The rows of the micro-block are written back IN PLACE below, into the very entries every other warp has just read
+    // as D: all loads must have completed before the first store (without this barrier a warp that is late with its
+    // loads sees a mixture of C and L values - observed as non-reproducible results once 1024 blocks keep every SM busy).
+    __syncthreads();
+    if (panel_thread) {
       const int npiv = min(8, max(0, bf - c0));
       const int rl = R - c0;               // < 8: this row lies inside the micro-block
       double dvs[8], invs[8];              // pivots and their inverse roots (bookkeeping after the chain, off its path)
