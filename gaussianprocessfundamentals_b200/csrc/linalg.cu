@@ -8,6 +8,7 @@
 //                the pieces of dNLL/dK = 1/2 (K^-1 - alpha alpha^T) that TF's Cholesky gradient produces for
 //                Optimizer/Fitter.py:124-158.
 //   run_trsv     standalone forward/back substitution (CovarianceMatrix.py:260-262) for get_L_alpha().
+#include <algorithm>
 #include <cstdlib>
 #include "gemm.cuh"
 #include "internal.h"
@@ -22,13 +23,20 @@ namespace gpb {
 // A[r0:, r0:] -= P P^T for r0 = (kp+kb)*128, lower tiles, tile columns restricted to [c_lo, c_hi) so that the look-ahead
 // driver can split the update across streams.  kb = 2 halves the number of passes over the far trailing matrix and the
 // per-tile epilogue cost per flop (k = 256: 31 TFLOP/s against 28 at k = 128).
+// sep != 0: the carried row of a matrix whose n is a multiple of 128 is NOT part of the tiles (it would open a tile row of
+// its own - 1 useful row in 64 - which costs 14 .. 50 % of the update of the small trailing matrices of a batch);
+// carried_row_kernel applies the same product to it.
+__device__ __forceinline__ bool carried_row_separate(const GpbMat& d, int sep) {
+  return sep && d.aug && (d.n % GPB_NB) == 0;
+}
+
 struct GeoSyrk {
   const GpbMat* mats;
-  int kp, kb, c_lo, c_hi;
+  int kp, kb, c_lo, c_hi, sep;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
-    const int nrows = d.n + d.aug;
+    const int nrows = d.n + (carried_row_separate(d, sep) ? 0 : d.aug);
     const int r0 = (kp + kb) * GPB_NB;
     if (r0 >= nrows || r0 > d.n) return false;   // every block of the panel must be a full pivot block
     const int Tm = (nrows - r0 + BM - 1) / BM;
@@ -52,12 +60,12 @@ struct GeoSyrk {
 // (in place: a CTA owns all 128 columns of its rows, so BN must be 128)
 struct GeoPanel {
   const GpbMat* mats;
-  int k;
+  int k, sep;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "the in-place panel product needs full-width tiles");
     const GpbMat& d = mats[b.z];
-    const int nrows = d.n + d.aug;
+    const int nrows = d.n + (carried_row_separate(d, sep) ? 0 : d.aug);
     const int r0 = (k + 1) * GPB_NB;
     if (r0 > d.n) return false;  // block k is not a full pivot block
     const int i0 = r0 + b.x * BM;
@@ -772,6 +780,46 @@ __global__ void diag_copy_kernel(const GpbMat* __restrict__ mats, int k0) {
   }
 }
 
+// The carried right-hand side y^T (row n) of the matrices whose tiles exclude it (carried_row_separate):
+//   mode 0 (after the diagonal block kp): row n of block column kp times inv(L_kk)^T, as the panel product does
+//   mode 1 (with the panel blocks kp .. kp + kb - 1): row n of the trailing columns [c_lo, c_hi) (128-wide, from
+//          (kp + kb) * 128) minus z_panel . P[j, :]^T - including the element (n, n), which accumulates -z^T z
+__global__ void __launch_bounds__(256) carried_row_kernel(const GpbMat* __restrict__ mats, int kp, int kb, int c_lo, int c_hi,
+                                                          int mode) {
+  __shared__ double zs[2 * GPB_NB];
+  const GpbMat d = mats[blockIdx.z];
+  if (!carried_row_separate(d, 1)) return;
+  const int n = d.n;
+  const size_t ld = d.ld;
+  const int tid = threadIdx.x;
+  double* rown = d.A + n;                                   // rown[j * ld] = A[n, j]
+  if (mode == 0) {
+    if ((kp + 1) * GPB_NB > n || blockIdx.x != 0) return;   // block kp is the last one: the diagonal kernel owned the row
+    if (tid < GPB_NB) zs[tid] = rown[(size_t)(kp * GPB_NB + tid) * ld];
+    __syncthreads();
+    if (tid < GPB_NB) {
+      const double* Wg = d.Wd + (size_t)kp * GPB_NB * GPB_NB;
+      double acc = 0.0;
+      for (int j = 0; j <= tid; ++j) acc = fma(zs[j], Wg[tid + j * GPB_NB], acc);
+      rown[(size_t)(kp * GPB_NB + tid) * ld] = acc;
+    }
+    return;
+  }
+  const int r0 = (kp + kb) * GPB_NB;
+  if (r0 > n) return;
+  const int kw = kb * GPB_NB;
+  for (int q = tid; q < kw; q += 256) zs[q] = rown[(size_t)(kp * GPB_NB + q) * ld];
+  __syncthreads();
+  const int j = r0 + c_lo * GPB_NB + blockIdx.x * 256 + tid;           // column of row n = row of the panel
+  const long long j_hi = (long long)r0 + (long long)c_hi * GPB_NB;
+  if (j > n || j >= j_hi) return;
+  const double* P = d.A + j + (size_t)kp * GPB_NB * ld;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int q = 0; q < kw; ++q) acc = fma(zs[q], P[(size_t)q * ld], acc);
+  rown[(size_t)j * ld] -= acc;
+}
+
 // nll = 1/2 z^T z + sum log diag L + 1/2 n log(2 pi)   (Metrics/LogLikelihood.py:39-49,65); also gathers z
 __global__ void finalize_kernel(const GpbMat* __restrict__ mats, double log2pi) {
   const GpbMat d = mats[blockIdx.x];
@@ -1133,23 +1181,44 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   };
   // launches of the critical path that would not fill one wave with 64-row tiles use 32-row tiles: half the tile latency
   auto small = [&](int rows) { return (long long)((rows + BM - 1) / BM) * B <= 160 && quarter_tiles(); };
+  // Without look-ahead (batches, small matrices) the carried row of matrices with n = 0 mod 128 is kept out of the GEMM
+  // tiles and updated by carried_row_kernel right behind every panel product / trailing update (same stream).
+  const int sep = lookahead ? 0 : 1;
+  auto carried = [&](int kp, int kb, int c_lo, int c_hi, int mode, cudaStream_t st) -> cudaError_t {
+    if (!sep || !aug) return cudaSuccess;
+    const int r0 = (kp + (mode ? kb : 1)) * GPB_NB;
+    if (r0 > n_max) return cudaSuccess;                                 // the largest matrix decides the grid only
+    const long long avail = (long long)n_max - ((long long)r0 + (long long)c_lo * GPB_NB) + 1;
+    const long long want = (long long)(c_hi - c_lo) * GPB_NB;
+    const int cols = mode ? (int)std::min(avail, want) : GPB_NB;
+    if (cols <= 0) return cudaSuccess;
+    carried_row_kernel<<<dim3(mode ? (cols + 255) / 256 : 1, 1, B), 256, 0, st>>>(dm, kp, kb, c_lo, c_hi, mode);
+    ++g_launches;
+    return cudaGetLastError();
+  };
   auto panel = [&](int k) -> cudaError_t {
     const int rows = nrows - (k + 1) * GPB_NB;
-    if (small(rows)) return launch_cfg<CfgQuarter, false, false>(GeoPanel{dm, k}, dim3((rows + 31) / 32, 1, B), ms);
-    const int Tm = (rows + BM - 1) / BM;
-    return launch_cfg<Cfg, false, false>(GeoPanel{dm, k}, dim3(Tm, 1, B), ms);
+    if (small(rows)) {
+      GPB_CK((launch_cfg<CfgQuarter, false, false>(GeoPanel{dm, k, sep}, dim3((rows + 31) / 32, 1, B), ms)));
+    } else {
+      const int Tm = (rows + BM - 1) / BM;
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k, sep}, dim3(Tm, 1, B), ms)));
+    }
+    return carried(k, 1, 0, 0, 0, ms);
   };
   auto syrk = [&](int kp, int kb, int c_lo, int c_hi, cudaStream_t st, bool bulk) -> cudaError_t {
     const int rows = nrows - (kp + kb) * GPB_NB;
     if (rows <= 0) return cudaSuccess;
     if (!bulk && c_hi - c_lo == 1 && small(rows)) {
       const int Tq = (rows + 31) / 32;
-      return launch_cfg<CfgQuarter, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi},
-                                                  dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false);
+      GPB_CK((launch_cfg<CfgQuarter, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep},
+                                                   dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false)));
+    } else {
+      const int Tm = (rows + BM - 1) / BM;
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep},
+                                            dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk)));
     }
-    const int Tm = (rows + BM - 1) / BM;
-    return launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi},
-                                         dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk);
+    return carried(kp, kb, c_lo, c_hi, 1, st);
   };
   int step = 0;
   for (int k = 0; k < nblk;) {
