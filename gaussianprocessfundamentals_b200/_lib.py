@@ -61,6 +61,8 @@ SIGNATURES = {
                                           ctypes.c_int]),
     "gpb_debug_diag_clocks": (ctypes.c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "gpb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "gpb_trace_begin": (ctypes.c_int, [ctypes.c_void_p]),
+    "gpb_trace_end": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
 }
 
 _lib = None

@@ -14,10 +14,68 @@
 #include "internal.h"
 #include "jit.h"
 #include "program.cuh"
+#include "trace.h"
 
 namespace gpb {
 std::atomic<long long> g_launches{0};
+
+// ---- launch timeline (trace.h) ---------------------------------------------------------------------------------------
+struct TraceRec { const char* tag; int a, b; cudaStream_t s; cudaEvent_t e0, e1; };
+static std::mutex g_trace_mu;
+static std::vector<TraceRec> g_trace;
+static std::atomic<bool> g_trace_on{false};
+static cudaEvent_t g_trace_origin = nullptr;
+bool trace_active() { return g_trace_on.load(std::memory_order_relaxed); }
+int trace_open(const char* tag, cudaStream_t s, int a, int b) {
+  TraceRec r{tag, a, b, s, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, s);
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  g_trace.push_back(r);
+  return (int)g_trace.size() - 1;
+}
+void trace_close(int id, cudaStream_t s) {
+  cudaEvent_t e1;
+  { std::lock_guard<std::mutex> lk(g_trace_mu); e1 = g_trace[id].e1; }
+  cudaEventRecord(e1, s);
+}
 }  // namespace gpb
+
+extern "C" int gpb_trace_begin(void* stream) {
+  std::lock_guard<std::mutex> lk(gpb::g_trace_mu);
+  for (auto& r : gpb::g_trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  gpb::g_trace.clear();
+  if (!gpb::g_trace_origin && cudaEventCreate(&gpb::g_trace_origin) != cudaSuccess) return 1;
+  if (cudaEventRecord(gpb::g_trace_origin, (cudaStream_t)stream) != cudaSuccess) return 1;
+  gpb::g_trace_on = true;
+  return 0;
+}
+// one line per span: "tag a b stream start_us end_us" (times relative to gpb_trace_begin; stream = index by first use)
+extern "C" int gpb_trace_end(char* buf, size_t capacity, size_t* needed) {
+  gpb::g_trace_on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  std::lock_guard<std::mutex> lk(gpb::g_trace_mu);
+  std::vector<cudaStream_t> streams;
+  std::string out;
+  char line[160];
+  for (auto& r : gpb::g_trace) {
+    int si = -1;
+    for (size_t i = 0; i < streams.size(); ++i) if (streams[i] == r.s) si = (int)i;
+    if (si < 0) { streams.push_back(r.s); si = (int)streams.size() - 1; }
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventElapsedTime(&t0, gpb::g_trace_origin, r.e0);
+    cudaEventElapsedTime(&t1, gpb::g_trace_origin, r.e1);
+    snprintf(line, sizeof line, "%s %d %d %d %.1f %.1f\n", r.tag, r.a, r.b, si, t0 * 1e3, t1 * 1e3);
+    out += line;
+  }
+  if (needed) *needed = out.size() + 1;
+  if (buf && capacity) {
+    const size_t ncopy = out.size() < capacity - 1 ? out.size() : capacity - 1;
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return 0;
+}
 
 // one NVTX range per stage of an evaluation (host side: brackets the launches of the stage on the timeline)
 struct NvtxRange {
@@ -366,15 +424,23 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   p->own_streams = false;
   int prio_lo = 0, prio_hi = 0;
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  // four priority levels when the device has them (numerically lower = more urgent; B200: 0 .. -5): critical path >
+  // second-next panel's columns > bulk update > overlapped inverse.  With fewer levels neighbours share one.
+  const int span = prio_lo - prio_hi;
+  const int pr_mid = prio_hi + (span >= 3 ? span / 3 : (span >= 1 ? 1 : 0));
+  const int pr_side = span >= 3 ? prio_lo - 1 : prio_lo;
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.crit, cudaStreamNonBlocking, prio_hi);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.side, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.mid, cudaStreamNonBlocking, pr_mid);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.side, cudaStreamNonBlocking, pr_side);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.inv, cudaStreamNonBlocking, prio_lo);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&p->ex.ev_e[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_g[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_c[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_b[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_d[i], cudaEventDisableTiming);
   }
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
   p->n_graphs = 0; p->graphs_off = 0; p->gstream = nullptr;
   {
@@ -697,12 +763,14 @@ void gpb_plan_destroy(gpb_plan_t* p) {
   if (!p) return;
   if (p->own_streams) {
     cudaStreamDestroy(p->ex.crit);
+    cudaStreamDestroy(p->ex.mid);
     cudaStreamDestroy(p->ex.side);
     cudaStreamDestroy(p->ex.inv);
     for (int i = 0; i < 2; ++i) {
       cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_c[i]);
+      cudaEventDestroy(p->ex.ev_b[i]); cudaEventDestroy(p->ex.ev_d[i]);
     }
-    for (int i = 0; i < 3; ++i) cudaEventDestroy(p->ex.ev_join[i]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ex.ev_join[i]);
     cudaEventDestroy(p->ex.ev_fork);
     for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);
     if (p->gstream) { cudaStreamDestroy(p->gstream); cudaEventDestroy(p->g_in); cudaEventDestroy(p->g_out); }

@@ -39,6 +39,7 @@
 #include "dist.h"
 #include "gemm.cuh"
 #include "internal.h"
+#include "trace.h"
 
 namespace gpb {
 
@@ -413,8 +414,10 @@ __global__ void __launch_bounds__(1024) dist_finalize_kernel(const GpbMat* __res
 #define GPB_TR(x) do { if (!(x)) return cudaErrorUnknown; } while (0)
 
 template <class Cfg, class Geo>
-static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
+static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false, const char* tag = "dgemm",
+                              int ta = 0) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  TraceSpan span(tag, s, ta, (int)(grid.x * grid.y * grid.z));
   static bool attr_set = false;
   if (!attr_set) {
     GPB_CK(cudaFuncSetAttribute(gemm_kernel<Cfg, false, false, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -489,27 +492,32 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     }
     if (full && q == qk) {
       const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
-      GPB_CK((launch_geo<Cfg>(GeoDistPanel{dm, k, P, p}, dim3(Tm, 1, 1), cs)));
+      GPB_CK((launch_geo<Cfg>(GeoDistPanel{dm, k, P, p}, dim3(Tm, 1, 1), cs, false, "panel", k)));
     }
     // ---- exchange: pack own tiles, broadcast every process row's segment, unpack the others' tiles ------------
     const int t0 = (P > 1 && full) ? 1 : 0;                // the diagonal tile already travelled when P > 1
     const bool ship_wd = (t0 == 0);                        // inv(L_kk) is replicated too: the later stages need all of them
     if (nt - t0 > 0) {
       if (q == qk) {
+        TraceSpan span("pack", cs, k, nt - t0);
         panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 0);
         ++g_launches;
       }
       if (ship_wd && D.rank == diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(st_wd, Wk); ++g_launches; }
-      GPB_TR(D.tr->group_start());
-      if (ship_wd) GPB_TR(D.tr->broadcast(st_wd, st_wd, TILE_ELEMS, diag_owner, cs));
-      for (int o = 0; o < P; ++o) {
-        int first = seg_base[o], cnt = seg_count[o];
-        if (t0 == 1 && o == pk) { first += 1; cnt -= 1; }  // skip the diagonal tile (slot 0 of its owner's segment)
-        if (cnt <= 0) continue;
-        double* b = st + (size_t)first * TILE_ELEMS;
-        GPB_TR(D.tr->broadcast(b, b, (size_t)cnt * TILE_ELEMS, o * Q + qk, cs));
+      {
+        TraceSpan span("bcast", cs, k, nt - t0);
+        GPB_TR(D.tr->group_start());
+        if (ship_wd) GPB_TR(D.tr->broadcast(st_wd, st_wd, TILE_ELEMS, diag_owner, cs));
+        for (int o = 0; o < P; ++o) {
+          int first = seg_base[o], cnt = seg_count[o];
+          if (t0 == 1 && o == pk) { first += 1; cnt -= 1; }  // skip the diagonal tile (slot 0 of its owner's segment)
+          if (cnt <= 0) continue;
+          double* b = st + (size_t)first * TILE_ELEMS;
+          GPB_TR(D.tr->broadcast(b, b, (size_t)cnt * TILE_ELEMS, o * Q + qk, cs));
+        }
+        GPB_TR(D.tr->group_end());
       }
-      GPB_TR(D.tr->group_end());
+      TraceSpan span("unpack", cs, k, nt - t0);
       panel_copy_kernel<<<nt - t0, 256, 0, cs>>>(h.A, (long long)ld, nrows, k, t0, st, map, p, qk, q, 1);
       ++g_launches;
       if (ship_wd && D.rank != diag_owner) { tile_copy_kernel<<<8, 256, 0, cs>>>(Wk, st_wd); ++g_launches; }
@@ -517,12 +525,12 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     return cudaSuccess;
   };
   const int Jend = nbr;
-  auto syrk = [&](int kp, int kb, int Jlo, int Jhi, cudaStream_t s) -> cudaError_t {
+  auto syrk = [&](int kp, int kb, int Jlo, int Jhi, cudaStream_t s, const char* tag) -> cudaError_t {
     if (Jhi > Jend) Jhi = Jend;
     const int nc = count_owned_cols(Jlo, Jhi, Q, q);
     if (nc == 0) return cudaSuccess;
     const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
-    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true);
+    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true, tag, kp);
   };
   const bool wide = potrf_outer_blocks(n) > 1;             // 256-wide outer panels (two panels per far update)
   int step = 0;
@@ -534,7 +542,7 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     if (wide && (k + 2) * GPB_NB <= n) {
       // block column k+1 received its far update of the previous outer step on the side stream
       if (step > 0) { GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(step - 1) & 1], 0)); waited = true; }
-      GPB_CK(syrk(k, 1, k + 1, k + 2, cs));                // strip: block column k+1 <- panel k
+      GPB_CK(syrk(k, 1, k + 1, k + 2, cs, "strip"));               // strip: block column k+1 <- panel k
       GPB_CK(factor_block(k + 1));
       kb = 2;
     }
@@ -543,11 +551,11 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     //      columns the next outer step touches, then the rest
     const int J1 = k + kb;
     if (step > 0 && !waited) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_g[(step - 1) & 1], 0));
-    GPB_CK(syrk(k, kb, J1, J1 + 1, cs));
+    GPB_CK(syrk(k, kb, J1, J1 + 1, cs, "col"));
     GPB_CK(cudaStreamWaitEvent(ss, ex.ev_e[step & 1], 0));
-    GPB_CK(syrk(k, kb, J1 + 1, J1 + 1 + kb, ss));
+    GPB_CK(syrk(k, kb, J1 + 1, J1 + 1 + kb, ss, "next"));
     GPB_CK(cudaEventRecord(ex.ev_g[step & 1], ss));
-    GPB_CK(syrk(k, kb, J1 + 1 + kb, Jend, ss));
+    GPB_CK(syrk(k, kb, J1 + 1 + kb, Jend, ss, "bulk"));
     k += kb;
     ++step;
   }
@@ -657,8 +665,9 @@ __global__ void __launch_bounds__(256) tri_diag_store_kernel(const GpbMat* __res
 }
 
 template <class Cfg, bool AKM, bool BKM, class Geo>
-static cudaError_t launch_geo2(const Geo& geo, dim3 grid, cudaStream_t s) {
+static cudaError_t launch_geo2(const Geo& geo, dim3 grid, cudaStream_t s, const char* tag = "dgemm2", int ta = 0) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  TraceSpan span(tag, s, ta, (int)(grid.x * grid.y * grid.z));
   static bool attr_set = false;
   if (!attr_set) {
     GPB_CK(cudaFuncSetAttribute(gemm_kernel<Cfg, AKM, BKM, Geo>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -688,7 +697,7 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     const int nJ_lt = own_cols_upto(I - 1, world, rank);
     const int nJ_le = own_cols_upto(I, world, rank);
     if (nJ_le == 0) return cudaSuccess;
-    if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), s)));
+    if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), s, "tri_diag", I)));
     tri_diag_store_kernel<<<nJ_le, 256, 0, s>>>(dm, scratch, I, world, rank);
     ++g_launches;
     return cudaGetLastError();
@@ -697,7 +706,7 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     const int nJ = own_cols_upto(I + kb - 1, world, rank);
     if (nJ == 0 || row_hi <= row_lo) return cudaSuccess;
     return launch_geo2<Cfg, false, true>(GeoDistTriUpdate{dm, I, kb, row_lo, row_hi, world, rank},
-                                         dim3((row_hi - row_lo + Cfg::BM - 1) / Cfg::BM, nJ, 1), s);
+                                         dim3((row_hi - row_lo + Cfg::BM - 1) / Cfg::BM, nJ, 1), s, "tri_upd", I);
   };
   const bool wide = potrf_outer_blocks(n) > 1;             // two block rows per far update (k = 256), as in the factorisation
   for (int I = 0; I < nblk;) {
@@ -713,6 +722,7 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   }
   // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
   for (int J0 = 0; J0 < nblk; J0 += 64) {
+    TraceSpan span("w_bcast", s, J0, 64);
     GPB_TR(D.tr->group_start());
     for (int J = J0; J < std::min(nblk, J0 + 64); ++J) {
       const int cols = std::min(GPB_NB, n - J * GPB_NB);
@@ -728,7 +738,7 @@ cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   const int nblk = (h.n + GPB_NB - 1) / GPB_NB;
   const int nJ = own_cols_upto(nblk - 1, D.world, D.rank);
   const int Tm = (h.n + Cfg::BM - 1) / Cfg::BM;
-  return launch_geo2<Cfg, true, true>(GeoDistLauum{dm, D.world, D.rank}, dim3(Tm, nJ, 1), s);
+  return launch_geo2<Cfg, true, true>(GeoDistLauum{dm, D.world, D.rank}, dim3(Tm, nJ, 1), s, "lauum", 0);
 }
 
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s) {

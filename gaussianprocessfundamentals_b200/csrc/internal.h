@@ -12,13 +12,16 @@ extern std::atomic<long long> g_launches;  // kernels launched since load (gpb_l
 struct Exec {
   cudaStream_t main;       // the caller's stream
   cudaStream_t crit;       // high priority: diagonal block, panel, next panel column (the critical path)
+  cudaStream_t mid;        // medium priority: the update of the second-next outer panel's columns (depth-2 look-ahead)
   cudaStream_t side;       // low priority: the bulk of the trailing update
-  cudaStream_t inv;        // low priority: the triangular inverse of what is already final (overlapped with the tail)
+  cudaStream_t inv;        // lowest priority: the triangular inverse of what is already final (overlapped with the tail)
   cudaEvent_t ev_c[2];     // block columns final (recorded on crit, waited on by inv)
   cudaEvent_t ev_fork;     // caller's stream -> crit / side
   cudaEvent_t ev_e[2];     // panel k ready (recorded on crit)
-  cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side)
-  cudaEvent_t ev_join[3];  // crit / side / inv -> caller's stream
+  cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side; distributed factorisation)
+  cudaEvent_t ev_b[2];     // second-next outer panel's columns updated by outer step s (recorded on mid)
+  cudaEvent_t ev_d[2];     // bulk update of outer step s complete (recorded on side)
+  cudaEvent_t ev_join[4];  // crit / side / inv / mid -> caller's stream
 };
 
 // ---- linalg.cu ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include "gemm.cuh"
 #include "internal.h"
+#include "trace.h"
 
 namespace gpb {
 
@@ -949,9 +950,16 @@ static bool cfg_half() {
 // persistent = CTAs walk up to TILES_PER_CTA tiles each (equal-cost tiles: the trailing update); otherwise one CTA per
 // tile under the hardware scheduler (tiles of very different k-length: triangular inverse, W^T W)
 template <class Cfg, bool AKM, bool BKM, class Geo>
-static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false) {
-  constexpr int TILES_PER_CTA = 2;   // measured best on B200 (1: 425 ms, 2: 415 ms, 4: 416 ms, 8: 423 ms potrf at n = 32768)
+static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s, bool persistent = false, const char* tag = "gemm",
+                              int ta = 0) {
+  // Tiles per CTA of a persistent (bulk) launch.  Two tiles keep the operand pipeline running across a tile boundary
+  // (measured at n = 32768: 1: 425 ms, 2: 415 ms, 4: 416 ms, 8: 423 ms potrf), but CTAs of two tiles quantise a launch of
+  // a few waves badly (n = 8192, 1849 tiles: 925 CTAs = 3.1 waves of 296 -> 4 x 2 tile times against 7 x 1), so launches
+  // below 8 waves use one tile per CTA (potrf at n = 8192 8.47 -> 8.29 ms).
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  const long long tiles = (long long)grid.x * grid.y * grid.z;
+  const int TILES_PER_CTA = tiles >= 8LL * 296 ? 2 : 1;
+  TraceSpan span(tag, s, ta, (int)tiles);
   gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent ? TILES_PER_CTA : 1), Cfg::THREADS,
                                    Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
@@ -1036,6 +1044,11 @@ int potrf_outer_blocks(int n_max) { return kb_max(n_max); }
 // ---------------------------------------------------------------------------------------------------------------
 struct TrtriSched {
   int n = 0, nblk = 0, nlev = 0, copied = 0;
+  // Levels above smax wait for the end of the factorisation.  A tile of level s contracts over up to s elements - 536 us
+  // at s = 4096 - and stream priorities act only when a CTA retires: with T(4096) resident on every SM each kernel of the
+  // factorisation's serial chain waited for a slot, and the diagonal-block kernel (a whole SM) for two (launch timeline at
+  // n = 8192: block columns 48 .. 52 took 1.9 ms instead of 0.3).  GPB_INV_SMAX overrides (0: no limit).
+  long long smax = 1024;
   int nextT[24], nextW[24], nsub[24];
   void init(int n_) {
     n = n_; nblk = (n + GPB_NB - 1) / GPB_NB; nlev = 0; copied = 0;
@@ -1044,6 +1057,9 @@ struct TrtriSched {
       nextT[nlev] = nextW[nlev] = 0;
       ++nlev;
     }
+    static long long env_smax = -1;
+    if (env_smax < 0) { const char* e = getenv("GPB_INV_SMAX"); env_smax = e ? atoll(e) : 1024; }
+    smax = env_smax > 0 ? env_smax : (1LL << 40);
   }
   bool lower_done(int li, long long X) const {            // everything below level li that starts left of X is launched
     const long long Xc = X < n ? X : n;
@@ -1075,6 +1091,7 @@ struct TrtriSched {
       }
       for (int li = 0; li < nlev; ++li) {
         const long long s = (long long)GPB_NB << li;
+        if (s > smax && fc < n) break;
         int cnt = 0;
         while (nextT[li] + cnt < nsub[li]) {
           const long long rA = 2 * s * (nextT[li] + cnt) + s;
@@ -1104,17 +1121,18 @@ struct TrtriDeviceLauncher {        // the scheduler's tasks as kernel launches 
   const GpbMat* dm;
   cudaStream_t st;
   cudaError_t copy(int k0, int cnt) {
+    TraceSpan span("inv_copy", st, k0, cnt);
     diag_copy_kernel<<<dim3(cnt, 1), 1024, 0, st>>>(dm, k0);
     ++g_launches;
     return cudaGetLastError();
   }
   cudaError_t T(int s, int p0, int cnt) {
     const int tiles = (s / Cfg::BM) * (s / Cfg::BN);
-    return launch_cfg<Cfg, false, true>(GeoTrtriT{dm, s, p0}, dim3(tiles, cnt, 1), st);
+    return launch_cfg<Cfg, false, true>(GeoTrtriT{dm, s, p0}, dim3(tiles, cnt, 1), st, false, "inv_T", s);
   }
   cudaError_t W(int s, int p0, int cnt) {
     const int tiles = (s / Cfg::BM) * (s / Cfg::BN);
-    return launch_cfg<Cfg, false, true>(GeoTrtriW{dm, s, p0}, dim3(tiles, cnt, 1), st);
+    return launch_cfg<Cfg, false, true>(GeoTrtriW{dm, s, p0}, dim3(tiles, cnt, 1), st, false, "inv_W", s);
   }
 };
 
@@ -1155,6 +1173,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
     GPB_CK(cudaStreamWaitEvent(ex.crit, ex.ev_fork, 0));
+    GPB_CK(cudaStreamWaitEvent(ex.mid, ex.ev_fork, 0));
     GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_fork, 0));
   }
   const bool fuse = lookahead && with_trtri && B == 1;
@@ -1175,12 +1194,13 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     return k < nblk && (k + 1) * GPB_NB <= n_max && nrows - (k + 1) * GPB_NB > 0;
   };
   auto diag = [&](int k) -> cudaError_t {
+    TraceSpan span("diag", ms, k, B);
     launch_diag(dm, B, k, ms);
     ++g_launches;
     return cudaGetLastError();
   };
   // launches of the critical path that would not fill one wave with 64-row tiles use 32-row tiles: half the tile latency
-  auto small = [&](int rows) { return (long long)((rows + BM - 1) / BM) * B <= 160 && quarter_tiles(); };
+  auto small = [&](long long rows) { return ((rows + BM - 1) / BM) * B <= 148 && quarter_tiles(); };
   // Without look-ahead (batches, small matrices) the carried row of matrices with n = 0 mod 128 is kept out of the GEMM
   // tiles and updated by carried_row_kernel right behind every panel product / trailing update (same stream).
   const int sep = lookahead ? 0 : 1;
@@ -1199,38 +1219,47 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   auto panel = [&](int k) -> cudaError_t {
     const int rows = nrows - (k + 1) * GPB_NB;
     if (small(rows)) {
-      GPB_CK((launch_cfg<CfgQuarter, false, false>(GeoPanel{dm, k, sep}, dim3((rows + 31) / 32, 1, B), ms)));
+      GPB_CK((launch_cfg<CfgQuarter, false, false>(GeoPanel{dm, k, sep}, dim3((rows + 31) / 32, 1, B), ms, false, "panel_q", k)));
     } else {
       const int Tm = (rows + BM - 1) / BM;
-      GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k, sep}, dim3(Tm, 1, B), ms)));
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoPanel{dm, k, sep}, dim3(Tm, 1, B), ms, false, "panel", k)));
     }
     return carried(k, 1, 0, 0, 0, ms);
   };
-  auto syrk = [&](int kp, int kb, int c_lo, int c_hi, cudaStream_t st, bool bulk) -> cudaError_t {
+  auto syrk = [&](int kp, int kb, int c_lo, int c_hi, cudaStream_t st, bool bulk, const char* tag) -> cudaError_t {
     const int rows = nrows - (kp + kb) * GPB_NB;
     if (rows <= 0) return cudaSuccess;
-    if (!bulk && c_hi - c_lo == 1 && small(rows)) {
+    if (!bulk && small((long long)rows * (c_hi - c_lo))) {
       const int Tq = (rows + 31) / 32;
       GPB_CK((launch_cfg<CfgQuarter, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep},
-                                                   dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false)));
+                                                   dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false, tag, kp)));
     } else {
       const int Tm = (rows + BM - 1) / BM;
       GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep},
-                                            dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk)));
+                                            dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk, tag, kp)));
     }
     return carried(kp, kb, c_lo, c_hi, 1, st);
   };
+  // Look-ahead of depth 2 over OUTER steps s (W = 1 or 2 block columns each).  The update of outer step s is split by
+  // target columns (128-wide tile columns of the trailing matrix):
+  //   A(s) = [0, W)    the next outer panel            critical stream, right behind the factorisation of step s
+  //   B(s) = [W, 2W)   the second-next outer panel     medium-priority stream
+  //   C(s) = [2W, ..)  the bulk                        low-priority stream
+  // A column receives the updates of the outer steps in order (C(s-2), B(s-1), A(s) - bitwise reproducible):
+  //   A(s) waits for B(s-1) (event ev_b), B(s) for all of C(s-1) (ev_d), C(s) follows C(s-1) on its stream; B(s) and C(s)
+  // wait for the panels of step s (ev_e).  The factorisation of step s+1 therefore depends on C(s-2), not on C(s-1): the
+  // critical path runs up to two outer steps ahead of the bulk, and the low-priority stream runs bulk update after bulk
+  // update with nothing in between (with depth 1 the small "next columns" launch sat between two bulk updates on the same
+  // stream: 48 of 390 us per outer step at n = 8192, one partially filled wave).
+  const int W = kb_max(n_max, B);
   int step = 0;
   for (int k = 0; k < nblk;) {
     GPB_CK(diag(k));
     if (!full_with_rows(k)) { GPB_CK(inverse_progress(k + 1)); ++k; continue; }
     GPB_CK(panel(k));
     int kb = 1;
-    bool waited = false;
-    if (kb_max(n_max, B) > 1 && full_with_rows(k + 1)) {
-      // block column k+1 received its far update from the previous outer step on the side stream
-      if (lookahead && step > 0) { GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(step - 1) & 1], 0)); waited = true; }
-      GPB_CK(syrk(k, 1, 0, 1, ms, false));          // block column k+1 <- panel k (inside the 256-wide outer panel)
+    if (W > 1 && full_with_rows(k + 1)) {
+      GPB_CK(syrk(k, 1, 0, 1, ms, false, "strip"));   // block column k+1 <- panel k (inside the 256-wide outer panel)
       GPB_CK(diag(k + 1));
       GPB_CK(panel(k + 1));
       kb = 2;
@@ -1239,15 +1268,22 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     const int rows = nrows - (k + kb) * GPB_NB;
     const int Tn = (rows + GPB_NB - 1) / GPB_NB;
     if (!lookahead) {
-      GPB_CK(syrk(k, kb, 0, Tn, ms, true));
+      GPB_CK(syrk(k, kb, 0, Tn, ms, true, "bulk"));
     } else {
-      if (step > 0 && !waited) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_g[(step - 1) & 1], 0));
-      GPB_CK(syrk(k, kb, 0, 1, ms, false));                       // the next diagonal block's column
       GPB_CK(cudaEventRecord(ex.ev_e[step & 1], ms));
-      GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[step & 1], 0));
-      GPB_CK(syrk(k, kb, 1, 1 + kb, ex.side, false));             // the columns the next outer step touches first
-      GPB_CK(cudaEventRecord(ex.ev_g[step & 1], ex.side));
-      GPB_CK(syrk(k, kb, 1 + kb, Tn, ex.side, true));
+      if (step > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_b[(step - 1) & 1], 0));
+      GPB_CK(syrk(k, kb, 0, W, ms, false, "A"));
+      if (Tn > W) {
+        GPB_CK(cudaStreamWaitEvent(ex.mid, ex.ev_e[step & 1], 0));
+        if (step > 0) GPB_CK(cudaStreamWaitEvent(ex.mid, ex.ev_d[(step - 1) & 1], 0));
+        GPB_CK(syrk(k, kb, W, 2 * W, ex.mid, false, "B"));
+      }
+      GPB_CK(cudaEventRecord(ex.ev_b[step & 1], ex.mid));
+      if (Tn > 2 * W) {
+        GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[step & 1], 0));
+        GPB_CK(syrk(k, kb, 2 * W, Tn, ex.side, true, "bulk"));
+      }
+      GPB_CK(cudaEventRecord(ex.ev_d[step & 1], ex.side));
     }
     k += kb;
     ++step;
@@ -1261,8 +1297,10 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   if (lookahead) {
     GPB_CK(cudaEventRecord(ex.ev_join[0], ex.crit));
     GPB_CK(cudaEventRecord(ex.ev_join[1], ex.side));
+    GPB_CK(cudaEventRecord(ex.ev_join[3], ex.mid));
     GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
     GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+    GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[3], 0));
   }
   return cudaSuccess;
 }
@@ -1273,6 +1311,7 @@ cudaError_t run_potrf(const GpbMat* dm, int B, int n_max, int aug, bool lookahea
 }
 
 cudaError_t run_diag(const GpbMat* dm, int B, int k, cudaStream_t s) {
+  TraceSpan span("diag", s, k, B);
   launch_diag(dm, B, k, s);
   ++g_launches;
   return cudaGetLastError();

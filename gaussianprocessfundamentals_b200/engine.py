@@ -408,6 +408,27 @@ def launch_count() -> int:
     return int(_lib.load().gpb_launch_count())
 
 
+class trace:
+    """with engine.trace() as t: plan.eval(...)  ->  t.spans = [(tag, a, b, stream, start_us, end_us)] of every launch
+    (developer tool, gpb_trace_begin / gpb_trace_end; not usable around eval_host's graph replay)"""
+
+    def __enter__(self):
+        self.spans = []
+        _lib.check(_lib.load().gpb_trace_begin(_stream_ptr()), "gpb_trace_begin")
+        return self
+
+    def __exit__(self, *exc):
+        lib = _lib.load()
+        need = ctypes.c_size_t()
+        _lib.check(lib.gpb_trace_end(None, 0, ctypes.byref(need)), "gpb_trace_end")
+        buf = ctypes.create_string_buffer(max(1, need.value))
+        _lib.check(lib.gpb_trace_end(buf, len(buf), None), "gpb_trace_end")
+        for line in buf.value.decode().splitlines():
+            tag, a, b, st, t0, t1 = line.split()
+            self.spans.append((tag, int(a), int(b), int(st), float(t0), float(t1)))
+        return False
+
+
 def _padded(t: torch.Tensor) -> torch.Tensor:
     """row-major 2-d tensor with an even number of columns and 16-byte aligned storage (copy only if needed)"""
     t = t.contiguous()

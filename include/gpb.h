@@ -192,6 +192,12 @@ int gpb_trtri_schedule(int n, const long long* final_cols, int n_steps, int* tas
 int gpb_microbench(int kind, int iters, int blocks, void* stream);
 /* Developer builds only (-DGPB_DIAG_CLOCKS=1): SM clock counts of the phases of the last diagonal-block launch; -1 otherwise. */
 int gpb_debug_diag_clocks(long long* out8);
+/* Developer tool: launch timeline of the multi-stream drivers (the reference has no counterpart; nsys is not available on
+ * the pool).  Between gpb_trace_begin and gpb_trace_end every launch of gpb_plan_eval is bracketed by two CUDA events on
+ * its stream.  gpb_trace_end synchronises the device and writes one text line per launch:
+ * "tag a b stream start_us end_us" (times relative to gpb_trace_begin).  Not usable under stream capture.              */
+int gpb_trace_begin(void* stream);
+int gpb_trace_end(char* buf, size_t capacity, size_t* needed);
 
 #ifdef __cplusplus
 }
