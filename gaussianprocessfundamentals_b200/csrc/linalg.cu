@@ -9,12 +9,15 @@
 //                Optimizer/Fitter.py:124-158.
 //   run_trsv     standalone forward/back substitution (CovarianceMatrix.py:260-262) for get_L_alpha().
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 #include "gemm.cuh"
 #include "internal.h"
 #include "trace.h"
 
 namespace gpb {
+
+constexpr int GPB_KB_MAX = 8;   // widest outer panel of the factorisation in 128-blocks (GPB_POTRF_KB)
 
 // ---------------------------------------------------------------------------------------------------------------
 // GEMM geometries (tile<BM, BN>() fills the job of the calling CTA; BN is always 128 = GPB_NB)
@@ -787,7 +790,7 @@ __global__ void diag_copy_kernel(const GpbMat* __restrict__ mats, int k0) {
 //          (kp + kb) * 128) minus z_panel . P[j, :]^T - including the element (n, n), which accumulates -z^T z
 __global__ void __launch_bounds__(256) carried_row_kernel(const GpbMat* __restrict__ mats, int kp, int kb, int c_lo, int c_hi,
                                                           int mode) {
-  __shared__ double zs[2 * GPB_NB];
+  __shared__ double zs[GPB_KB_MAX * GPB_NB];
   const GpbMat d = mats[blockIdx.z];
   if (!carried_row_separate(d, 1)) return;
   const int n = d.n;
@@ -1007,28 +1010,40 @@ static bool quarter_tiles() {
   return v == 1;
 }
 
-// outer panel width of the factorisation in 128-blocks.  Measured on B200 (potrf, ms, kb = 1 / 2): n = 4096 3.16 / 3.43,
-// 8192 10.08 / 9.91, 16384 56.9 / 52.9, 32768 411 / 380 - the wider panel pays once the far update dominates.
-// GPB_POTRF_KB=1|2 overrides.
-// Batches of independent GPs have no critical path to protect: the wider panel pays from n = 1024 on (C3 256 x n = 2048:
-// potrf 33.7 -> 32.1 ms, C4 1024 x n = 1024: 21.8 -> 21.1 ms).
-static int kb_max(int n_max, int B = 1) {
+// Outer panel width of the factorisation in 128-blocks, chosen per outer step from the rows that remain (`rem`).  The
+// panels of an outer step hit the far trailing matrix together (k = 128 W: 28 TFLOP/s at W = 1, 31 at 2, 33 at 4) but
+// lengthen the serial chain inside the outer panel, so the width shrinks as the trailing matrix does.  Measured on B200
+// (potrf ms, fixed W = 1 / 2 / 3 / 4): n = 4096 3.16 / 3.43, 8192 10.08 / 8.44 / 8.50 / 9.02, 16384 - / 51.4 / 50.6 / 50.1,
+// 32768 - / 381.5 / 372.1 / 367.6.  GPB_POTRF_KB=1..8 forces one width; GPB_POTRF_T2 / _T4 / _T8 move the thresholds.
+// Batches of independent GPs have no critical path to protect: wide panels pay from n = 1024 on (C3 256 x n = 2048:
+// potrf 33.7 / 31.0 / 30.6 ms at W = 1 / 2 / 4, C4 1024 x n = 1024: 21.8 / 19.4 / 19.1).
+static int kb_forced() {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("GPB_POTRF_KB");
-    forced = e ? ((e[0] == '1') ? 1 : 2) : 0;
+    forced = e ? std::max(1, std::min(GPB_KB_MAX, atoi(e))) : 0;
   }
-  if (forced) return forced;
-  if (B >= 8) return n_max >= 1024 ? 2 : 1;
-  return n_max >= 6144 ? 2 : 1;
+  return forced;
 }
+static long long env_rows(const char* name, long long dflt) {
+  const char* e = getenv(name);
+  return e ? atoll(e) : dflt;
+}
+static int kb_for(long long rem, int B) {
+  if (kb_forced()) return kb_forced();
+  if (B >= 8) return rem >= 1024 ? 4 : 1;
+  static const long long t2 = env_rows("GPB_POTRF_T2", 5120), t4 = env_rows("GPB_POTRF_T4", 10240),
+                         t8 = env_rows("GPB_POTRF_T8", 24576);
+  return rem >= t8 ? 8 : rem >= t4 ? 4 : rem >= t2 ? 2 : 1;
+}
+static int kb_max(int n_max, int B = 1) { return kb_for(n_max, B); }
 
 // Blocked right-looking Cholesky.  Diagonal blocks and panels are 128 wide; two consecutive panels are applied to the
 // far trailing matrix together (k = 256).  With look-ahead (one large matrix) the critical path - diagonal block, panel,
 // the strip update of the second block column, and the first far column - runs on a high-priority stream so that its
 // few CTAs are dispatched ahead of the thousands of queued trailing-update CTAs of the low-priority stream, which does
 // the columns the next outer step needs first and then the bulk.
-int potrf_outer_blocks(int n_max) { return kb_max(n_max); }
+int potrf_outer_blocks(int n_max) { return std::min(2, kb_max(n_max)); }   // the distributed drivers: 1 or 2
 
 // ---------------------------------------------------------------------------------------------------------------
 // Triangular inverse overlapped with the factorisation (one large matrix).  The recursive-doubling inverse is a task
@@ -1251,18 +1266,30 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
   // critical path runs up to two outer steps ahead of the bulk, and the low-priority stream runs bulk update after bulk
   // update with nothing in between (with depth 1 the small "next columns" launch sat between two bulk updates on the same
   // stream: 48 of 390 us per outer step at n = 8192, one partially filled wave).
-  const int W = kb_max(n_max, B);
+  // widths of the outer steps (decided up front: the split of an update follows the NEXT two outer panels)
+  std::vector<int> width;
+  for (int k = 0; k < nblk;) {
+    if (!full_with_rows(k)) { ++k; continue; }
+    const int W = B >= 8 ? kb_for(n_max, B) : kb_for((long long)n_max - (long long)k * GPB_NB, B);
+    int kb = 1;
+    while (kb < W && full_with_rows(k + kb)) ++kb;
+    width.push_back(kb);
+    k += kb;
+  }
   int step = 0;
   for (int k = 0; k < nblk;) {
     GPB_CK(diag(k));
     if (!full_with_rows(k)) { GPB_CK(inverse_progress(k + 1)); ++k; continue; }
     GPB_CK(panel(k));
+    const int W = width[step];
     int kb = 1;
-    if (W > 1 && full_with_rows(k + 1)) {
-      GPB_CK(syrk(k, 1, 0, 1, ms, false, "strip"));   // block column k+1 <- panel k (inside the 256-wide outer panel)
-      GPB_CK(diag(k + 1));
-      GPB_CK(panel(k + 1));
-      kb = 2;
+    // inside the outer panel the block columns are factorised left-looking: column k + kb receives the kb finished
+    // panels in one rank-(128 kb) strip update, then its diagonal block and panel follow
+    while (kb < W) {
+      GPB_CK(syrk(k, kb, 0, 1, ms, false, "strip"));
+      GPB_CK(diag(k + kb));
+      GPB_CK(panel(k + kb));
+      ++kb;
     }
     GPB_CK(inverse_progress(k + kb));
     const int rows = nrows - (k + kb) * GPB_NB;
@@ -1270,18 +1297,22 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
     if (!lookahead) {
       GPB_CK(syrk(k, kb, 0, Tn, ms, true, "bulk"));
     } else {
+      // columns of the next outer panel / of the second-next one; the last block column (partial or carried row) has no
+      // outer step of its own and rides with whatever range reaches it
+      const int W1 = step + 1 < (int)width.size() ? width[step + 1] : Tn;
+      const int W2 = step + 2 < (int)width.size() ? width[step + 2] : Tn;
       GPB_CK(cudaEventRecord(ex.ev_e[step & 1], ms));
       if (step > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_b[(step - 1) & 1], 0));
-      GPB_CK(syrk(k, kb, 0, W, ms, false, "A"));
-      if (Tn > W) {
+      GPB_CK(syrk(k, kb, 0, W1, ms, false, "A"));
+      if (Tn > W1) {
         GPB_CK(cudaStreamWaitEvent(ex.mid, ex.ev_e[step & 1], 0));
         if (step > 0) GPB_CK(cudaStreamWaitEvent(ex.mid, ex.ev_d[(step - 1) & 1], 0));
-        GPB_CK(syrk(k, kb, W, 2 * W, ex.mid, false, "B"));
+        GPB_CK(syrk(k, kb, W1, W1 + W2, ex.mid, false, "B"));
       }
       GPB_CK(cudaEventRecord(ex.ev_b[step & 1], ex.mid));
-      if (Tn > 2 * W) {
+      if (Tn > W1 + W2) {
         GPB_CK(cudaStreamWaitEvent(ex.side, ex.ev_e[step & 1], 0));
-        GPB_CK(syrk(k, kb, 2 * W, Tn, ex.side, true, "bulk"));
+        GPB_CK(syrk(k, kb, W1 + W2, Tn, ex.side, true, "bulk"));
       }
       GPB_CK(cudaEventRecord(ex.ev_d[step & 1], ex.side));
     }
