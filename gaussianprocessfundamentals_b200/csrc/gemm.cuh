@@ -167,6 +167,37 @@ __device__ __forceinline__ void cp_async16_full(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
 
+// ---- bulk-copy (TMA engine) operand staging: the BULK variant of the mainloop -------------------------------------
+// One `cp.async.bulk.shared.global` per k-row of an MN-major slab (BM or BN contiguous doubles, 512 B / 1 KB) into the
+// same padded stage layout, issued by the lanes of warp 0 and completed on one mbarrier per stage (complete_tx), instead
+// of 12 LDGSTS + address adds per thread per slab.  No tensor map is needed (the rows of a column-major panel are
+// contiguous), and the padded pitch that keeps the DMMA fragment loads bank-conflict free survives - a tiled
+// `cp.async.bulk.tensor` box would be dense (pitch 512 B: 4-way conflicts; SWIZZLE_128B only reaches 2-way for f64).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+constexpr int G_BULK_EXTRA = 64;   // bytes behind the stage buffers: G_STAGES mbarriers
+
 // Tile loop of a CTA.  A CTA walks the virtual grid `vg` (the grid a one-tile-per-CTA launch would use) with stride
 // gridDim.x and keeps ONE cp.async pipeline running across tile boundaries: with fewer CTAs than tiles (persistent
 // launch) the first operand slabs of tile i+1 are in flight while tile i finishes, so a tile costs its k-steps plus its
@@ -174,8 +205,9 @@ __device__ __forceinline__ void cp_async16_full(void* smem, const void* gmem) {
 // scheduler.  Full tiles (the overwhelming majority) take a fast path whose per-slab load issue is one address add
 // and one LDGSTS per 16-byte chunk and whose epilogue has no bounds checks; edge tiles keep the zero-filling loads.
 // Geometry functors map a virtual block index to a TileJob: `bool Geo::tile<BM, BN>(TileJob&, const dim3& b)`.
-template <class Cfg, bool AKM, bool BKM, class Geo>
+template <class Cfg, bool AKM, bool BKM, class Geo, bool BULK = false>
 __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
+  static_assert(!BULK || (!AKM && !BKM && G_BK == 16), "bulk staging: MN-major operands, 16 k-rows = 16 lanes each");
   extern __shared__ __align__(16) double gsm[];
   constexpr int BM = Cfg::BM, BN = Cfg::BN, T = Cfg::THREADS, FM = Cfg::FM, FN = Cfg::FN;
   constexpr int STAGE = Cfg::A_TILE + Cfg::B_TILE;
@@ -191,6 +223,16 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
   int a_r0, a_c0, a_soff, b_r0, b_c0, b_soff;
   FA::setup(tid, a_r0, a_c0, a_soff);
   FB::setup(tid, b_r0, b_c0, b_soff);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gsm + G_STAGES * STAGE);   // BULK: one mbarrier per stage
+  unsigned bulk_mask = 0, phase_mask = 0;                                 // stage filled by bulk copies / its phase parity
+  if constexpr (BULK) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < G_STAGES; ++s) mbar_init(&full[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
 
   // next valid tile at or after idx
   auto fetch = [&](unsigned& idx, TileJob& J) -> bool {
@@ -223,12 +265,26 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
     l_fast = (Jl.mrem == BM) && (Jl.nrem == BN) && ((Jl.khi - Jl.klo) % G_BK == 0);
     l_pa = AKM ? Jl.A + Jl.klo + a_c0 + (size_t)a_r0 * Jl.lda : Jl.A + a_c0 + (size_t)(Jl.klo + a_r0) * Jl.lda;
     l_pb = BKM ? Jl.B + Jl.klo + b_c0 + (size_t)b_r0 * Jl.ldb : Jl.B + b_c0 + (size_t)(Jl.klo + b_r0) * Jl.ldb;
+    if constexpr (BULK) {     // lane q of warp 0 copies k-row q & 15 of A (q < 16) or B: its own row pointer
+      l_pa = Jl.A + (size_t)(Jl.klo + (lane & 15)) * Jl.lda;
+      l_pb = Jl.B + (size_t)(Jl.klo + (lane & 15)) * Jl.ldb;
+    }
   };
   next_load_tile();
   auto issue = [&](int stage) {
     if (l_ok) {
       double* Ns = gsm + stage * STAGE;
-      if (l_fast) {
+      if (BULK && l_fast) {
+        bulk_mask |= 1u << stage;
+        if (warp == 0) {
+          if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)((BM + BN) * G_BK * sizeof(double)));
+          __syncwarp();
+          if (lane < 16) bulk_g2s(Ns + lane * (BM + 4), l_pa, BM * (unsigned)sizeof(double), &full[stage]);
+          else bulk_g2s(Ns + Cfg::A_TILE + (lane - 16) * (BN + 4), l_pb, BN * (unsigned)sizeof(double), &full[stage]);
+        }
+        l_pa += (size_t)G_BK * Jl.lda;
+        l_pb += (size_t)G_BK * Jl.ldb;
+      } else if (l_fast) {
 #pragma unroll
         for (int q = 0; q < FA::NQ; ++q)
           cp_async16_full(Ns + a_soff + q * FA::S_Q, l_pa + (size_t)(q * FA::QROWS) * Jl.lda);
@@ -238,6 +294,7 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
         l_pa += AKM ? (size_t)G_BK : (size_t)G_BK * Jl.lda;
         l_pb += BKM ? (size_t)G_BK : (size_t)G_BK * Jl.ldb;
       } else {
+        if constexpr (BULK) bulk_mask &= ~(1u << stage);
         load_tile<AKM, BM, T>(Ns, Jl.A, Jl.lda, Jl.mrem, Jl.klo + l_kt * G_BK, Jl.khi, tid);
         load_tile<BKM, BN, T>(Ns + Cfg::A_TILE, Jl.B, Jl.ldb, Jl.nrem, Jl.klo + l_kt * G_BK, Jl.khi, tid);
       }
@@ -276,6 +333,10 @@ __device__ __forceinline__ void gemm_stream(const Geo& geo, const dim3 vg) {
 
     for (int kt = 0; kt < nk; ++kt) {
       cp_async_wait<G_STAGES - 2>();
+      if constexpr (BULK) {
+        const int st = step % G_STAGES;
+        if ((bulk_mask >> st) & 1u) { mbar_wait(&full[st], (phase_mask >> st) & 1u); phase_mask ^= 1u << st; }
+      }
       __syncthreads();
       issue((step + G_STAGES - 1) % G_STAGES);
       const double* As = gsm + (step % G_STAGES) * STAGE;
@@ -348,6 +409,11 @@ __device__ __forceinline__ bool tri_map_grouped(unsigned idx, int Tm, int R, int
 template <class Cfg, bool AKM, bool BKM, class Geo>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_kernel(const Geo geo, const dim3 vgrid) {
   gemm_stream<Cfg, AKM, BKM, Geo>(geo, vgrid);
+}
+// the same tile loop with bulk-copy operand staging (MN-major operands only; launched with SMEM_BYTES + G_BULK_EXTRA)
+template <class Cfg, class Geo>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_bulk_kernel(const Geo geo, const dim3 vgrid) {
+  gemm_stream<Cfg, false, false, Geo, true>(geo, vgrid);
 }
 
 // CTAs of a launch over `vgrid` tiles.  max_tiles_per_cta = 1: one CTA per tile.  Larger values let a CTA keep its

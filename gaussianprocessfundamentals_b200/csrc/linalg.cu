@@ -9,6 +9,7 @@
 //                Optimizer/Fitter.py:124-158.
 //   run_trsv     standalone forward/back substitution (CovarianceMatrix.py:260-262) for get_L_alpha().
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include <cstdlib>
 #include "gemm.cuh"
@@ -950,6 +951,13 @@ static bool cfg_half() {
   return g_cfg_half == 1;
 }
 
+// GPB_TMA=1: the trailing updates of the factorisation stage their operands with bulk copies (gemm_bulk_kernel)
+static bool bulk_staging() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_TMA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 // persistent = CTAs walk up to TILES_PER_CTA tiles each (equal-cost tiles: the trailing update); otherwise one CTA per
 // tile under the hardware scheduler (tiles of very different k-length: triangular inverse, W^T W)
 template <class Cfg, bool AKM, bool BKM, class Geo>
@@ -963,6 +971,14 @@ static cudaError_t launch_cfg(const Geo& geo, dim3 grid, cudaStream_t s, bool pe
   const long long tiles = (long long)grid.x * grid.y * grid.z;
   const int TILES_PER_CTA = tiles >= 8LL * 296 ? 2 : 1;
   TraceSpan span(tag, s, ta, (int)tiles);
+  if constexpr (!AKM && !BKM && std::is_same<Geo, GeoSyrk>::value && !std::is_same<Cfg, CfgQuarter>::value) {
+    if (bulk_staging()) {
+      gemm_bulk_kernel<Cfg, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent ? TILES_PER_CTA : 1), Cfg::THREADS,
+                                   Cfg::SMEM_BYTES + G_BULK_EXTRA, s>>>(geo, grid);
+      ++g_launches;
+      return cudaGetLastError();
+    }
+  }
   gemm_kernel<Cfg, AKM, BKM, Geo><<<persistent_ctas(grid, Cfg::MIN_CTAS, persistent ? TILES_PER_CTA : 1), Cfg::THREADS,
                                    Cfg::SMEM_BYTES, s>>>(geo, grid);
   ++g_launches;
@@ -996,6 +1012,8 @@ cudaError_t linalg_init() {
   }
   GPB_CK(set_smem_all<CfgBig>());
   GPB_CK(set_smem_all<CfgHalf>());
+  GPB_CK(cudaFuncSetAttribute(gemm_bulk_kernel<CfgBig, GeoSyrk>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBig::SMEM_BYTES + G_BULK_EXTRA));
+  GPB_CK(cudaFuncSetAttribute(gemm_bulk_kernel<CfgHalf, GeoSyrk>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgHalf::SMEM_BYTES + G_BULK_EXTRA));
   GPB_CK((set_smem<CfgQuarter, false, false, GeoSyrk>()));
   GPB_CK((set_smem<CfgQuarter, false, false, GeoPanel>()));
   GPB_CK(cudaFuncSetAttribute(diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
@@ -1033,7 +1051,7 @@ static int kb_for(long long rem, int B) {
   if (kb_forced()) return kb_forced();
   if (B >= 8) return rem >= 1024 ? 4 : 1;
   static const long long t2 = env_rows("GPB_POTRF_T2", 5120), t4 = env_rows("GPB_POTRF_T4", 10240),
-                         t8 = env_rows("GPB_POTRF_T8", 24576);
+                         t8 = env_rows("GPB_POTRF_T8", 20480);
   return rem >= t8 ? 8 : rem >= t4 ? 4 : rem >= t2 ? 2 : 1;
 }
 static int kb_max(int n_max, int B = 1) { return kb_for(n_max, B); }
