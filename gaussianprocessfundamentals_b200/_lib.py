@@ -56,6 +56,10 @@ SIGNATURES = {
     "gpb_dist_destroy": (None, [ctypes.c_void_p]),
     "gpb_plan_create_dist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
     "gpb_dist_owner": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "gpb_dist_col_width": (ctypes.c_int, [ctypes.c_int]),
+    "gpb_dist_owner_w": (ctypes.c_int, [ctypes.c_int] * 5),
+    "gpb_dist_owned_cols": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                           ctypes.c_int]),
     "gpb_dist_panel_segments": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_int_p, c_int_p]),
     "gpb_trtri_schedule": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, c_int_p,
                                           ctypes.c_int]),

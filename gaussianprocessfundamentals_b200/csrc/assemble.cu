@@ -26,7 +26,7 @@ struct AsmArgs {
   double* K; long long ld;
   int lower_only;
   const double* y; int aug;   // aug: row n receives y^T, (n,n) receives 0
-  int own_P, own_Q, own_p, own_q;   // distributed plans: write only the 128-blocks this process owns (own_P == 0: all)
+  int own_P, own_Q, own_p, own_q, own_W;   // distributed plans: write only the 128-blocks this process owns (own_P == 0: all)
 };
 
 __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, int T) {
@@ -34,8 +34,8 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   bool own_main = true, own_aug = a.aug && ti == T - 1;
   if (a.own_P) {
     constexpr int R = GPB_NB / A_T;
-    own_main = ((ti / R) % a.own_P == a.own_p) && ((tj / R) % a.own_Q == a.own_q);
-    own_aug = own_aug && ((int)(a.n / GPB_NB) % a.own_P == a.own_p) && ((tj / R) % a.own_Q == a.own_q);
+    own_main = ((ti / R) % a.own_P == a.own_p) && ((tj / R / a.own_W) % a.own_Q == a.own_q);
+    own_aug = own_aug && ((int)(a.n / GPB_NB) % a.own_P == a.own_p) && ((tj / R / a.own_W) % a.own_Q == a.own_q);
     if (!own_main && !own_aug) return;
   }
   int32_t* s_code = reinterpret_cast<int32_t*>(asm_smem);
@@ -82,7 +82,7 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
   if (a.aug && ti == T - 1 && tj == T - 1 && tid == 0) {
     // element (n, n) accumulates -z^T z; in a distributed plan it belongs to block (n / 128, n / 128)
     const int bn = (int)(a.n / GPB_NB);
-    if (!a.own_P || (bn % a.own_P == a.own_p && bn % a.own_Q == a.own_q)) a.K[a.n + a.n * a.ld] = 0.0;
+    if (!a.own_P || (bn % a.own_P == a.own_p && (bn / a.own_W) % a.own_Q == a.own_q)) a.K[a.n + a.n * a.ld] = 0.0;
   }
 }
 
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __r
   a.code = d.code; a.n_ops = d.n_ops; a.dim = d.dim; a.cp_mode = d.cp_mode;
   a.X = d.X; a.X2 = nullptr; a.n = d.n; a.m = d.n; a.hp = d.hp; a.n_hp = d.n_hp; a.noise = d.noise;
   a.K = d.A; a.ld = d.ld; a.lower_only = 1; a.y = d.y; a.aug = d.aug;
-  a.own_P = d.own_P; a.own_Q = d.own_Q; a.own_p = d.own_p; a.own_q = d.own_q;
+  a.own_P = d.own_P; a.own_Q = d.own_Q; a.own_p = d.own_p; a.own_q = d.own_q; a.own_W = d.own_W;
   assemble_tile(a, ti, tj, T);
 }
 
@@ -249,7 +249,7 @@ cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int c
   a.code = code_dev; a.n_ops = n_ops; a.dim = dim; a.cp_mode = cp_mode;
   a.X = X; a.X2 = X2; a.n = n; a.m = m; a.hp = hp_dev; a.n_hp = n_hp; a.noise = noise_dev;
   a.K = K; a.ld = ldk; a.lower_only = lower_only; a.y = nullptr; a.aug = 0;
-  a.own_P = a.own_Q = a.own_p = a.own_q = 0;
+  a.own_P = a.own_Q = a.own_p = a.own_q = 0; a.own_W = 1;
   const int Tm = (int)((n + A_T - 1) / A_T), Tn = (int)((m + A_T - 1) / A_T);
   if (Tm == 0 || Tn == 0) return cudaSuccess;
   const size_t smem = asm_smem_bytes(n_ops, n_hp, dim);

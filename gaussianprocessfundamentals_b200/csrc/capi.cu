@@ -430,6 +430,7 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   const int pr_mid = prio_hi + (span >= 3 ? span / 3 : (span >= 1 ? 1 : 0));
   const int pr_side = span >= 3 ? prio_lo - 1 : prio_lo;
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.crit, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.comm, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.mid, cudaStreamNonBlocking, pr_mid);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.side, cudaStreamNonBlocking, pr_side);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->ex.inv, cudaStreamNonBlocking, prio_lo);
@@ -439,7 +440,10 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_c[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_b[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_d[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_p[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_x[i], cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join_comm, cudaEventDisableTiming);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
   p->n_graphs = 0; p->graphs_off = 0; p->gstream = nullptr;
@@ -504,7 +508,7 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     d.n = (int)m.n; d.ld = m.ld; d.dim = g->dim; d.n_ops = g->n_ops; d.n_hp = g->n_hp; d.aug = 1;
     d.cp_mode = g->cp_mode; d.n_gtiles = m.n_gtiles;
     if (p->dist) {
-      d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q;
+      d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q; d.own_W = p->dist->OW;
       d.col_world = p->dist->world; d.col_rank = p->dist->rank;
     }
   }
@@ -586,16 +590,23 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }
       return fail_cuda(e, where);
     };
-    if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) {
+    const bool want_trtri = (stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI)) != 0;
+    const bool want_lauum = (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) != 0;
+    static int ovl_env = -1;     // GPB_DIST_OVERLAP=0: exchange of W after the inverse, W^T W as one launch
+    if (ovl_env < 0) { const char* oe = getenv("GPB_DIST_OVERLAP"); ovl_env = (oe && oe[0] == '0') ? 0 : 1; }
+    const bool overlap = want_trtri && want_lauum && ovl_env && s == p->ex.main;
+    if (want_trtri) {
       NvtxRange r("gpb:trtri(dist)");
-      int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), s), "trtri_dist");
+      int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), s, !overlap), "trtri_dist");
       if (rc) return rc;
-      CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
+      if (!overlap) CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
     }
-    if (stages & (GPB_STAGE_INVERSE | GPB_STAGE_LAUUM)) {
+    if (want_lauum) {
       NvtxRange r("gpb:lauum(dist)");
-      int rc = dist_rc(gpb::run_lauum_dist(dm, p->h_desc0, *p->dist, s), "lauum_dist");
+      int rc = overlap ? dist_rc(gpb::run_exchange_lauum_dist(dm, p->h_desc0, *p->dist, p->ex), "exchange+lauum_dist")
+                       : dist_rc(gpb::run_lauum_dist(dm, p->h_desc0, *p->dist, s), "lauum_dist");
       if (rc) return rc;
+      if (overlap) CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
     }
     if (stages & GPB_STAGE_GRAD) {
       NvtxRange r("gpb:grad(dist)");
@@ -763,13 +774,16 @@ void gpb_plan_destroy(gpb_plan_t* p) {
   if (!p) return;
   if (p->own_streams) {
     cudaStreamDestroy(p->ex.crit);
+    cudaStreamDestroy(p->ex.comm);
     cudaStreamDestroy(p->ex.mid);
     cudaStreamDestroy(p->ex.side);
     cudaStreamDestroy(p->ex.inv);
     for (int i = 0; i < 2; ++i) {
       cudaEventDestroy(p->ex.ev_e[i]); cudaEventDestroy(p->ex.ev_g[i]); cudaEventDestroy(p->ex.ev_c[i]);
       cudaEventDestroy(p->ex.ev_b[i]); cudaEventDestroy(p->ex.ev_d[i]);
+      cudaEventDestroy(p->ex.ev_p[i]); cudaEventDestroy(p->ex.ev_x[i]);
     }
+    cudaEventDestroy(p->ex.ev_join_comm);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ex.ev_join[i]);
     cudaEventDestroy(p->ex.ev_fork);
     for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);
@@ -826,6 +840,18 @@ void gpb_dist_destroy(gpb_dist_t* d) {
 int gpb_dist_owner(int I, int J, int P, int Q) {
   if (I < 0 || J < 0 || P < 1 || Q < 1) return -1;
   return (I % P) * Q + (J % Q);
+}
+
+int gpb_dist_col_width(int P) { return P < 1 ? -1 : gpb::dist_col_width(P); }
+
+int gpb_dist_owner_w(int I, int J, int P, int Q, int W) {
+  if (I < 0 || J < 0 || P < 1 || Q < 1 || W < 1) return -1;
+  return (I % P) * Q + ((J / W) % Q);
+}
+
+int gpb_dist_owned_cols(int J_lo, int J_hi, int Q, int q, int W, int* cols, int cap) {
+  if (J_lo < 0 || Q < 1 || q < 0 || q >= Q || W < 1 || (cap > 0 && !cols)) return -1;
+  return gpb::dist_owned_cols(J_lo, J_hi, Q, q, W, cols, cap);
 }
 
 int gpb_dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first) {

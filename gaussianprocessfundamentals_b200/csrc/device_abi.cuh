@@ -38,8 +38,9 @@ struct GpbMat {
   // (1, 1 = the NLL; the rank-3 batch aggregate of Metrics/LogLikelihood.py:62-63 uses 1/B and 1)
   double gw_quad, gw_logdet;
   int n, ld, dim, n_ops, n_hp, aug, cp_mode, n_gtiles;
-  // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, J mod own_Q); own_P == 0: all
-  int own_P, own_Q, own_p, own_q;
+  // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, (J / own_W) mod own_Q) -
+  // block columns are dealt out in groups of own_W (the outer panel of the factorisation); own_P == 0: all
+  int own_P, own_Q, own_p, own_q, own_W;
   // gradient stages of a distributed plan: block column J belongs to rank J mod col_world (col_world == 0: all)
   int col_world, col_rank;
 };

@@ -92,6 +92,16 @@ static bool nccl_ok(ncclResult_t r, const char* where) {
   g_dist_err = std::string(where) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
   return false;
 }
+// Ownership width of the block columns.  P == 1 (the default grid 1 x N): groups of 2 block columns - the owner
+// factorises a whole 256-wide outer panel without any exchange inside it and ships it with ONE broadcast
+// (run_potrf_dist_cols).  P > 1: single block columns (run_potrf_dist).  GPB_DIST_OW=1|2|4 overrides for P == 1.
+int dist_col_width(int P) {
+  if (P != 1) return 1;
+  const char* e = getenv("GPB_DIST_OW");
+  const int v = e ? atoi(e) : 2;
+  return v < 1 ? 1 : (v > GPB_DIST_MAX_OW ? GPB_DIST_MAX_OW : v);
+}
+
 int dist_unique_id(unsigned char* id128) {
   if (!nccl_load()) return 1;
   NcclId id;
@@ -124,6 +134,7 @@ int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, D
   t->comm = comm;
   DistCtx* d = new DistCtx;
   d->tr = t; d->rank = rank; d->world = world; d->P = P; d->Q = Q; d->p = rank / Q; d->q = rank % Q;
+  d->OW = dist_col_width(P);
   *out = d;
   return 0;
 }
@@ -252,6 +263,7 @@ int dist_create_loopback(int world, int P, int Q, DistCtx** out) {
     t->w = w; t->rank = r;
     DistCtx* d = new DistCtx;
     d->tr = t; d->rank = r; d->world = world; d->P = P; d->Q = Q; d->p = r / Q; d->q = r % Q;
+    d->OW = dist_col_width(P);
     out[r] = d;
   }
   return 0;
@@ -346,18 +358,25 @@ struct GeoDistPanel {
   }
 };
 
+// block columns owned by process column q (groups of OW, dealt out cyclically over Q): how many lie below J, and the t-th
+__host__ __device__ inline int owned_cols_below(int J, int Q, int q, int OW) {
+  const int g = J / OW, r = J % OW;
+  const int groups = g > q ? (g - q + Q - 1) / Q : 0;       // owned groups q, q + Q, ... that end before group g
+  return groups * OW + ((g % Q == q) ? r : 0);
+}
+__host__ __device__ inline int owned_col_at(int t, int Q, int q, int OW) { return ((t / OW) * Q + q) * OW + t % OW; }
+
 // trailing update with panel k of the blocks (I, J) this rank owns, J in [J_lo, J_hi):  A[I, J] -= L[I, k] L[J, k]^T.
 // grid.y enumerates this rank's block columns of the range, grid.x the BM-row tiles from the diagonal block down.
 struct GeoDistSyrk {
   const GpbMat* mats;
-  int k, kb, J_lo, J_hi, P, Q, p, q;     // panel = block columns k .. k + kb - 1 (kb = 1 or 2)
+  int k, kb, J_lo, J_hi, P, Q, p, q, OW;   // panel = block columns k .. k + kb - 1
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "block columns are 128 wide");
     const GpbMat& d = mats[0];
     const int nrows = d.n + d.aug;
-    const int Jf = J_lo + ((q - J_lo) % Q + Q) % Q;     // first block column >= J_lo owned by process column q
-    const int Jb = Jf + (int)b.y * Q;
+    const int Jb = owned_col_at(owned_cols_below(J_lo, Q, q, OW) + (int)b.y, Q, q, OW);   // b.y-th own column >= J_lo
     if (Jb >= J_hi) return false;
     const int row = Jb * GPB_NB + (int)b.x * BM;
     if (row >= nrows) return false;
@@ -429,21 +448,32 @@ static cudaError_t launch_geo(const Geo& geo, dim3 grid, cudaStream_t s, bool pe
   return cudaGetLastError();
 }
 
-static int count_owned_cols(int J_lo, int J_hi, int Q, int q) {
+static int count_owned_cols(int J_lo, int J_hi, int Q, int q, int OW = 1) {
   if (J_hi <= J_lo) return 0;
-  const int Jf = J_lo + ((q - J_lo) % Q + Q) % Q;
-  return Jf < J_hi ? (J_hi - Jf + Q - 1) / Q : 0;
+  return owned_cols_below(J_hi, Q, q, OW) - owned_cols_below(J_lo, Q, q, OW);
+}
+
+// the enumeration GeoDistSyrk uses, on the host (C-ABI gpb_dist_owned_cols; CPU tests)
+int dist_owned_cols(int J_lo, int J_hi, int Q, int q, int OW, int* cols, int cap) {
+  const int nc = count_owned_cols(J_lo, J_hi, Q, q, OW);
+  const int t0 = owned_cols_below(J_lo, Q, q, OW);
+  for (int t = 0; t < nc && t < cap; ++t) cols[t] = owned_col_at(t0 + t, Q, q, OW);
+  return nc;
 }
 
 size_t dist_stage_bytes(int n) {
   const int nrows = n + 1;
   const int nt = (nrows + GPB_NB - 1) / GPB_NB;
-  return (size_t)(nt + 2) * TILE_ELEMS * sizeof(double);    // +1 slot for inv(L_kk), +1 spare
+  // +1 slot for inv(L_kk), +1 spare, per block column of an outer panel (up to GPB_DIST_MAX_OW travel together)
+  return (size_t)GPB_DIST_MAX_OW * (nt + 2) * TILE_ELEMS * sizeof(double);
 }
 
 // The distributed factorisation.  dm: device descriptor (one GpbMat), h: its host copy, stage[2]: staging buffers of
 // dist_stage_bytes(n) each.
+cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex);
+
 cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex) {
+  if (D.P == 1) return run_potrf_dist_cols(dm, h, D, stage, ex);
   using Cfg = CfgHalf;
   constexpr int BM = Cfg::BM;
   const int n = h.n, nrows = h.n + h.aug;
@@ -530,7 +560,7 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     const int nc = count_owned_cols(Jlo, Jhi, Q, q);
     if (nc == 0) return cudaSuccess;
     const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
-    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, P, Q, p, q}, dim3(Tm, nc, 1), s, true, tag, kp);
+    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, P, Q, p, q, 1}, dim3(Tm, nc, 1), s, true, tag, kp);
   };
   const bool wide = potrf_outer_blocks(n) > 1;             // 256-wide outer panels (two panels per far update)
   int step = 0;
@@ -563,6 +593,128 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  return cudaSuccess;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The factorisation on a 1 x Q grid (P == 1, the default).  Block columns are owned in groups of OW; outer step s
+// factorises group s = block columns [s OW, (s+1) OW) entirely on its owner (diagonal block, panel, left-looking strip
+// update of the next column of the group - no exchange inside the group) and ships all of it with ONE broadcast on a
+// communication stream of its own, so that
+//   * a panel travels once per OW block columns (one NCCL launch of OW x the bytes instead of OW launches),
+//   * the chain per outer step is  [factorise OW columns locally] -> broadcast -> [update the next group's columns on its
+//     owner]  instead of OW x (factorise -> broadcast -> update) with a hand-over between ranks at every block column,
+//   * the owner's own updates start from its local copy and do not wait for the broadcast.
+// Look-ahead of depth 2 as on one GPU: with the panels of step s every rank updates its own columns of group s+1 on
+// the critical stream (A), of group s+2 on the medium-priority stream (B) and the rest on the low-priority one (C);
+// A(s) waits for B(s-1), B(s) for C(s-1), so the owner of group s+1 starts factorising while bulk updates still run.
+// ---------------------------------------------------------------------------------------------------------------
+static int post_gate() {      // 0: off, 1: receivers only (default), 2: receivers and the sender
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_DIST_GATE"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex) {
+  using Cfg = CfgHalf;
+  constexpr int BM = Cfg::BM;
+  const int n = h.n, nrows = h.n + h.aug;
+  const int nblk = (n + GPB_NB - 1) / GPB_NB;              // pivot block columns
+  const int nbr = (nrows + GPB_NB - 1) / GPB_NB;           // block rows (the carried y row may add one)
+  const int Q = D.Q, q = D.q, OW = D.OW;
+  cudaStream_t cs = ex.crit, ms = ex.mid, ss = ex.side, xs = ex.comm;
+  GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
+  GPB_CK(cudaStreamWaitEvent(cs, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ms, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(xs, ex.ev_fork, 0));
+  const size_t ld = h.ld;
+  PanelMap map;
+  map.P = 1; map.seg_base[0] = 0; map.seg_first[0] = 0;
+  auto syrk = [&](int kp, int kb, int Jlo, int Jhi, cudaStream_t s, const char* tag) -> cudaError_t {
+    if (Jhi > nbr) Jhi = nbr;
+    const int nc = count_owned_cols(Jlo, Jhi, Q, q, OW);
+    if (nc == 0) return cudaSuccess;
+    const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
+    return launch_geo<Cfg>(GeoDistSyrk{dm, kp, kb, Jlo, Jhi, 1, Q, 0, q, OW}, dim3(Tm, nc, 1), s, true, tag, kp);
+  };
+  const int ngroups = (nblk + OW - 1) / OW;
+  for (int s = 0; s < ngroups; ++s) {
+    const int k0 = s * OW, kb = std::min(OW, nblk - k0), e = s & 1;
+    const int owner = s % Q;                               // == (k0 / OW) % Q
+    const bool mine = (q == owner);
+    double* st = stage[e];
+    size_t off[GPB_DIST_MAX_OW + 1];                       // exchange buffer: per block column its tiles, then inv(L_kk)
+    off[0] = 0;
+    for (int j = 0; j < kb; ++j) off[j + 1] = off[j] + (size_t)(nbr - (k0 + j) + 1) * TILE_ELEMS;
+    if (mine) {
+      for (int j = 0; j < kb; ++j) {
+        const int k = k0 + j;
+        if (j > 0) GPB_CK(syrk(k0, j, k, k + 1, cs, "strip"));     // column k <- the j panels of the group before it
+        GPB_CK(run_diag(dm, 1, k, cs));
+        if ((k + 1) * GPB_NB <= n) {                               // full pivot block: a panel exists below it
+          const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
+          GPB_CK((launch_geo<Cfg>(GeoDistPanel{dm, k, 1, 0}, dim3(Tm, 1, 1), cs, false, "panel", k)));
+        }
+      }
+      GPB_CK(cudaEventRecord(ex.ev_p[e], cs));
+      GPB_CK(cudaStreamWaitEvent(xs, ex.ev_p[e], 0));
+      if (s >= 2 && post_gate() >= 2) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_d[e], 0));   // see the receivers' gate below
+      TraceSpan span("pack", xs, k0, kb);
+      for (int j = 0; j < kb; ++j) {
+        const int k = k0 + j, nt = nbr - k;
+        panel_copy_kernel<<<nt, 256, 0, xs>>>(h.A, (long long)ld, nrows, k, 0, st + off[j], map, 0, q, q, 0);
+        tile_copy_kernel<<<8, 256, 0, xs>>>(st + off[j] + (size_t)nt * TILE_ELEMS, h.Wd + (size_t)k * TILE_ELEMS);
+        g_launches += 2;
+      }
+      GPB_CK(cudaGetLastError());
+    }
+    // A receiver posts its side of the broadcast only when its own bulk update of step s-2 has finished: that is when
+    // the owner of this group could start factorising it (its A(s-1) waits for B(s-2), which waits for C(s-3)), give or
+    // take one step of load balance.  Posted earlier, the NCCL kernel spins for the owner's data for milliseconds and
+    // its CTAs (whole register files) take 16 - 24 SMs away from the bulk update (launch timeline on 2 GPUs,
+    // n = 32768: receive spans of 4 - 5 ms per outer step, bulk update at 24 instead of 31 TFLOP/s).  GPB_DIST_GATE=0: off.
+    // Gating the sender the same way (GPB_DIST_GATE=2) measured slightly worse (2 GPUs: potrf 213.5 vs 210.4 ms).
+    if (s >= 2 && !mine && post_gate() >= 1) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_d[e], 0));
+    {
+      TraceSpan span("bcast", xs, k0, kb);
+      GPB_TR(D.tr->broadcast(st, st, off[kb], owner, xs));
+    }
+    if (!mine) {
+      TraceSpan span("unpack", xs, k0, kb);
+      for (int j = 0; j < kb; ++j) {
+        const int k = k0 + j, nt = nbr - k;
+        panel_copy_kernel<<<nt, 256, 0, xs>>>(h.A, (long long)ld, nrows, k, 0, st + off[j], map, 0, owner, q, 1);
+        tile_copy_kernel<<<8, 256, 0, xs>>>(h.Wd + (size_t)k * TILE_ELEMS, st + off[j] + (size_t)nt * TILE_ELEMS);
+        g_launches += 2;
+      }
+      GPB_CK(cudaGetLastError());
+    }
+    GPB_CK(cudaEventRecord(ex.ev_x[e], xs));
+    // ---- updates of the own columns with the kb panels of this group -------------------------------------------
+    const int J1 = k0 + kb;
+    if (J1 >= nbr) continue;
+    cudaEvent_t ready = mine ? ex.ev_p[e] : ex.ev_x[e];    // the owner's copy is complete before the broadcast
+    if (!mine) GPB_CK(cudaStreamWaitEvent(cs, ready, 0));
+    if (s > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_b[(s - 1) & 1], 0));
+    GPB_CK(syrk(k0, kb, J1, J1 + OW, cs, "A"));
+    GPB_CK(cudaStreamWaitEvent(ms, ready, 0));
+    if (s > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_d[(s - 1) & 1], 0));
+    GPB_CK(syrk(k0, kb, J1 + OW, J1 + 2 * OW, ms, "B"));
+    GPB_CK(cudaEventRecord(ex.ev_b[e], ms));
+    GPB_CK(cudaStreamWaitEvent(ss, ready, 0));
+    GPB_CK(syrk(k0, kb, J1 + 2 * OW, nbr, ss, "bulk"));
+    GPB_CK(cudaEventRecord(ex.ev_d[e], ss));
+  }
+  GPB_CK(cudaEventRecord(ex.ev_join[0], cs));
+  GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
+  GPB_CK(cudaEventRecord(ex.ev_join[3], ms));
+  GPB_CK(cudaEventRecord(ex.ev_join_comm, xs));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[3], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join_comm, 0));
   return cudaSuccess;
 }
 
@@ -624,9 +776,9 @@ struct GeoDistTriUpdate {   // X[r, J] += L[r, I .. I+kb) * X[I .. I+kb, J]  for
   }
 };
 
-struct GeoDistLauum {       // inv(K)[ti, J] = sum_{k >= ti} W[k, ti]^T W[k, J] for the own block columns J
+struct GeoDistLauum {       // inv(K)[ti, J] = sum_{k >= ti} W[k, ti]^T W[k, J] for the own block columns J, rows in [row_lo, row_hi)
   const GpbMat* mats;
-  int world, rank;
+  int world, rank, row_lo, row_hi;
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     static_assert(BN == GPB_NB, "block columns are 128 wide");
@@ -634,8 +786,8 @@ struct GeoDistLauum {       // inv(K)[ti, J] = sum_{k >= ti} W[k, ti]^T W[k, J] 
     const int Jb = rank + (int)b.y * world;
     const int col0 = Jb * GPB_NB;
     if (col0 >= d.n) return false;
-    const int row = col0 + (int)b.x * BM;                               // lower tiles: rows from the diagonal block down
-    if (row >= d.n) return false;
+    const int row = max(col0, row_lo) + (int)b.x * BM;                  // lower tiles: rows from the diagonal block down
+    if (row >= d.n || row >= row_hi) return false;
     const size_t ld = d.ld;
     J.A = d.A + (size_t)row * ld;
     J.B = d.A + (size_t)col0 * ld;
@@ -683,7 +835,7 @@ static int own_cols_upto(int J_incl, int world, int rank) {   // own block colum
   return J_incl < rank ? 0 : (J_incl - rank) / world + 1;
 }
 
-cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s) {
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s, bool exchange) {
   using Cfg = CfgHalf;
   const int n = h.n, world = D.world, rank = D.rank;
   const int nblk = (n + GPB_NB - 1) / GPB_NB;
@@ -720,6 +872,7 @@ cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
     GPB_CK(update(I, kb, (I + kb) * GPB_NB, n));
     I += kb;
   }
+  if (!exchange) return cudaSuccess;   // run_exchange_lauum_dist ships W chunk by chunk under the W^T W product
   // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
   for (int J0 = 0; J0 < nblk; J0 += 64) {
     TraceSpan span("w_bcast", s, J0, 64);
@@ -738,7 +891,45 @@ cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
   const int nblk = (h.n + GPB_NB - 1) / GPB_NB;
   const int nJ = own_cols_upto(nblk - 1, D.world, D.rank);
   const int Tm = (h.n + Cfg::BM - 1) / Cfg::BM;
-  return launch_geo2<Cfg, true, true>(GeoDistLauum{dm, D.world, D.rank}, dim3(Tm, nJ, 1), s, "lauum", 0);
+  return launch_geo2<Cfg, true, true>(GeoDistLauum{dm, D.world, D.rank, 0, nblk * GPB_NB}, dim3(Tm, nJ, 1), s, "lauum", 0);
+}
+
+// The exchange of W = inv(L) (every block column from its owner's Kinv into everybody's A) overlapped with
+// inv(K) = W^T W.  Block columns travel in ascending chunks on the communication stream; the tiles of inv(K) whose ROWS
+// lie in chunk c need the columns of W up to chunk c only (tile (I, J), J <= I, contracts columns I and J of W), so
+// their launch follows the arrival of chunk c while chunk c+1 is in flight.  No hazard: the product for chunk c writes
+// Kinv[rows of c, own columns <= c], the broadcast of chunk c+1 reads Kinv columns of c+1 and writes A columns of c+1.
+// Only the first chunk's transfer is exposed (n = 32768 on 8 GPUs: the exchange was 20 of 78 + 44 ms).
+cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, const Exec& ex) {
+  using Cfg = CfgHalf;
+  const int n = h.n, world = D.world, rank = D.rank;
+  const int nblk = (n + GPB_NB - 1) / GPB_NB;
+  const size_t ld = h.ld;
+  cudaStream_t s = ex.main, xs = ex.comm;
+  GPB_CK(cudaEventRecord(ex.ev_fork, s));
+  GPB_CK(cudaStreamWaitEvent(xs, ex.ev_fork, 0));
+  int chunk = (nblk + 7) / 8;                              // 8 chunks, at least 8 block columns each
+  if (chunk < 8) chunk = 8;
+  int c = 0;
+  for (int J0 = 0; J0 < nblk; J0 += chunk, ++c) {
+    const int J1 = std::min(nblk, J0 + chunk);
+    {
+      TraceSpan span("w_bcast", xs, J0, J1 - J0);
+      GPB_TR(D.tr->group_start());
+      for (int J = J0; J < J1; ++J) {
+        const int cols = std::min(GPB_NB, n - J * GPB_NB);
+        GPB_TR(D.tr->broadcast(h.Kinv + (size_t)J * GPB_NB * ld, h.A + (size_t)J * GPB_NB * ld, (size_t)cols * ld, J % world, xs));
+      }
+      GPB_TR(D.tr->group_end());
+    }
+    GPB_CK(cudaEventRecord(ex.ev_x[c & 1], xs));
+    GPB_CK(cudaStreamWaitEvent(s, ex.ev_x[c & 1], 0));
+    const int nJ = own_cols_upto(J1 - 1, world, rank);     // own block columns J <= the last row block of the chunk
+    if (nJ > 0)
+      GPB_CK((launch_geo2<Cfg, true, true>(GeoDistLauum{dm, world, rank, J0 * GPB_NB, J1 * GPB_NB},
+                                           dim3((J1 - J0) * GPB_NB / Cfg::BM, nJ, 1), s, "lauum", J0)));
+  }
+  return cudaSuccess;
 }
 
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s) {

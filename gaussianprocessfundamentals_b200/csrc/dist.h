@@ -23,9 +23,12 @@ struct Transport {
 struct DistCtx {
   Transport* tr;              // owned
   int rank, world, P, Q, p, q;  // rank = p * Q + q
+  int OW;                     // block columns are owned in groups of OW: block (I, J) belongs to (I mod P, (J / OW) mod Q)
 };
+#define GPB_DIST_MAX_OW 4
 
 const char* dist_last_error();
+int dist_col_width(int P);    // ownership width of the block columns on a P x Q grid (GPB_DIST_OW)
 int dist_unique_id(unsigned char* id128);
 int dist_create(const unsigned char* id128, int rank, int world, int P, int Q, DistCtx** out);
 // `world` contexts of one loop-back world (virtual ranks 0 .. world-1 on the current device); out[world]
@@ -33,8 +36,11 @@ int dist_create_loopback(int world, int P, int Q, DistCtx** out);
 void dist_destroy(DistCtx* d);
 void dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
 size_t dist_stage_bytes(int n);
+int dist_owned_cols(int J_lo, int J_hi, int Q, int q, int OW, int* cols, int cap);   // own block columns in [J_lo, J_hi)
 cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex);
-cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s);
+// exchange = false leaves W = inv(L) split by block column in Kinv (run_exchange_lauum_dist must follow)
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s, bool exchange);
+cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, const Exec& ex);
 cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, cudaStream_t s);
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s);
 cudaError_t run_finalize_dist(const GpbMat* dm, double log2pi, cudaStream_t s);

@@ -14,6 +14,7 @@ struct Exec {
   cudaStream_t crit;       // high priority: diagonal block, panel, next panel column (the critical path)
   cudaStream_t mid;        // medium priority: the update of the second-next outer panel's columns (depth-2 look-ahead)
   cudaStream_t side;       // low priority: the bulk of the trailing update
+  cudaStream_t comm;       // high priority: pack / broadcast / unpack of the distributed factorisation's panels
   cudaStream_t inv;        // lowest priority: the triangular inverse of what is already final (overlapped with the tail)
   cudaEvent_t ev_c[2];     // block columns final (recorded on crit, waited on by inv)
   cudaEvent_t ev_fork;     // caller's stream -> crit / side
@@ -21,6 +22,9 @@ struct Exec {
   cudaEvent_t ev_g[2];     // column k+2 updated by panel k (recorded on side; distributed factorisation)
   cudaEvent_t ev_b[2];     // second-next outer panel's columns updated by outer step s (recorded on mid)
   cudaEvent_t ev_d[2];     // bulk update of outer step s complete (recorded on side)
+  cudaEvent_t ev_p[2];     // outer panel factorised on its owner (recorded on crit, waited on by comm)
+  cudaEvent_t ev_x[2];     // outer panel available on this rank (recorded on comm)
+  cudaEvent_t ev_join_comm;  // comm -> caller's stream
   cudaEvent_t ev_join[4];  // crit / side / inv / mid -> caller's stream
 };
 

@@ -55,8 +55,8 @@ __device__ __forceinline__ void assemble_spec_body(const GpbMat* __restrict__ ma
   bool own_main = true, own_aug = d.aug && ti == T - 1;
   if (d.own_P) {   // distributed plan: write only the 128-blocks this process owns
     constexpr int R = GPB_NB / S_T;
-    own_main = ((ti / R) % d.own_P == d.own_p) && ((tj / R) % d.own_Q == d.own_q);
-    own_aug = own_aug && ((n / GPB_NB) % d.own_P == d.own_p) && ((tj / R) % d.own_Q == d.own_q);
+    own_main = ((ti / R) % d.own_P == d.own_p) && ((tj / R / d.own_W) % d.own_Q == d.own_q);
+    own_aug = own_aug && ((n / GPB_NB) % d.own_P == d.own_p) && ((tj / R / d.own_W) % d.own_Q == d.own_q);
     if (!own_main && !own_aug) return;
   }
   const int tid = threadIdx.x;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void assemble_spec_body(const GpbMat* __restrict__ ma
   }
   if (d.aug && ti == T - 1 && tj == T - 1 && tid == 0) {
     const int bn = n / GPB_NB;
-    if (!d.own_P || (bn % d.own_P == d.own_p && bn % d.own_Q == d.own_q)) d.A[n + (size_t)n * ld] = 0.0;
+    if (!d.own_P || (bn % d.own_P == d.own_p && (bn / d.own_W) % d.own_Q == d.own_q)) d.A[n + (size_t)n * ld] = 0.0;
   }
 }
 

@@ -328,7 +328,7 @@ class ProcessGrid:
         return 1, world
 
     def owner(self, I: int, J: int) -> int:
-        return (I % self.P) * self.Q + (J % self.Q)
+        return _lib.load().gpb_dist_owner_w(I, J, self.P, self.Q, _lib.load().gpb_dist_col_width(self.P))
 
     def __del__(self):
         try:
@@ -351,7 +351,7 @@ class VirtualGrid:
             self.p, self.q = rank // Q, rank % Q
 
         def owner(self, I: int, J: int) -> int:
-            return (I % self.P) * self.Q + (J % self.Q)
+            return _lib.load().gpb_dist_owner_w(I, J, self.P, self.Q, _lib.load().gpb_dist_col_width(self.P))
 
     def __init__(self, P: int, Q: int):
         require_cuda()

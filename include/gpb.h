@@ -146,7 +146,7 @@ void gpb_plan_destroy(gpb_plan_t* plan);
  * Statistics/CovarianceMatrix.py:247-265; LogLikelihood.get_metric, Metrics/LogLikelihood.py:30-65; the gradient of
  * Optimizer/Fitter.py:124-158) when one matrix is evaluated by several GPUs.
  *   factorisation : the 128 x 128 blocks of the lower triangle are owned 2D block-cyclically, block (I, J) by rank
- *                   (I mod P) * Q + (J mod Q); every finished panel and inverted diagonal block is broadcast
+ *                   (I mod P) * Q + ((J / W) mod Q) (W: gpb_dist_col_width); every finished panel and inverted diagonal block is broadcast
  *                   (ncclBroadcast), so all ranks end up with the complete factor L, z = L^-1 y and the same nll / info
  *   gradient      : W = L^-1, K^-1 = W^T W and the trace gradient are split by block column (J mod world), with one
  *                   exchange of W and one ncclAllReduce of the n_hp + 1 gradient entries; every rank gets the same grad
@@ -170,6 +170,13 @@ int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gp
  * panel k (tile t = block row k + t): process row o sends seg_count[o] tiles starting at slot seg_base[o], the first
  * of which is tile seg_first[o], the following ones P apart.                                                    */
 int gpb_dist_owner(int I, int J, int P, int Q);
+/* Block columns are dealt out in groups of W = gpb_dist_col_width(P): W = 2 on a 1 x Q grid (the owner factorises a
+ * 256-wide outer panel without any exchange inside it and ships it with one broadcast), W = 1 when P > 1.  Owner of
+ * block (I, J) for a given W: (I mod P) * Q + ((J / W) mod Q).  gpb_dist_owned_cols lists, ascending, the block columns
+ * of [J_lo, J_hi) that process column q owns (returns their number; at most cap are written).                    */
+int gpb_dist_col_width(int P);
+int gpb_dist_owner_w(int I, int J, int P, int Q, int W);
+int gpb_dist_owned_cols(int J_lo, int J_hi, int Q, int q, int W, int* cols, int cap);
 int gpb_dist_panel_segments(int k, int n_tiles, int P, int* seg_base, int* seg_count, int* seg_first);
 
 /* ---- utilities used by the host mirror and the tests --------------------------------------------------------- */

@@ -193,3 +193,24 @@ print("ok")
     env = dict(os.environ, GPB_POTRF_KB="2")
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("ow", ["1", "4"])
+def test_virtual_grid_column_group_widths_subprocess(ow):
+    """GPB_DIST_OW (read at grid creation): block columns owned one by one / in groups of four on 1 x Q grids - the
+    default (groups of two) is what the tests above run.  Sizes with a ragged last group and fewer groups than ranks."""
+    script = r"""
+import sys
+sys.path.insert(0, %r)
+from gaussianprocessfundamentals_b200 import engine as eng
+from tests.test_gpu_virtual_grid import run_case
+for (P, Q) in [(1, 2), (1, 3), (1, 4)]:
+    run_case(eng, 1100, 1, P, Q)
+    run_case(eng, 1280, 8, P, Q, check_oracle=False)
+    run_case(eng, 385, 1, P, Q, check_oracle=False)
+print("ok")
+""" % ROOT
+    # ow = 1 also runs the un-overlapped exchange of W (one exchange after the inverse, W^T W as one launch)
+    env = dict(os.environ, GPB_DIST_OW=ow, GPB_DIST_OVERLAP="0" if ow == "1" else "1")
+    out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

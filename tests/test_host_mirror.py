@@ -197,6 +197,21 @@ def test_distributed_layout_host_arithmetic():
                 # the staging order is a permutation of the panel's tiles, contiguous per process row
                 assert sorted(slots.values()) == list(range(nt))
     assert lib.gpb_dist_owner(-1, 0, 1, 1) == -1
+    # ownership in groups of W block columns (1 x Q grids: the owner factorises a whole outer panel)
+    assert lib.gpb_dist_col_width(1) in (1, 2, 4) and lib.gpb_dist_col_width(2) == 1
+    for Q in (1, 2, 3, 4, 8):
+        for W in (1, 2, 4):
+            for I in range(6):
+                for J in range(40):
+                    assert lib.gpb_dist_owner_w(I, J, 1, Q, W) == (J // W) % Q
+                    assert lib.gpb_dist_owner_w(I, J, 2, Q, W) == (I % 2) * Q + (J // W) % Q
+            for q in range(Q):
+                for lo in range(0, 23):
+                    for hi in (lo, lo + 1, lo + 2, lo + 7, 40):
+                        want = [J for J in range(lo, hi) if (J // W) % Q == q]
+                        buf = (ctypes.c_int * 64)()
+                        assert lib.gpb_dist_owned_cols(lo, hi, Q, q, W, buf, 64) == len(want)
+                        assert list(buf[:len(want)]) == want
     assert lib.gpb_dist_panel_segments(0, 4, 9, base, cnt, first) != 0      # P > 8 is refused
 
 

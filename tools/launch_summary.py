@@ -10,7 +10,12 @@ def main(path):
         lines = [ln for ln in f if not ln.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
-        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        full = row["Kernel Name"]
+        name = re.sub(r"\(.*", "", full).replace("void ", "")
+        geo = re.search(r"gpb::(Geo\w+)", full)
+        if geo:   # gemm_kernel<GemmCfg<BM, BN, ..>, AKM, BKM, Geo>: keep the tile shape and the geometry
+            dims = re.findall(r"\(int\)(\d+)", full)
+            name = "gemm<%sx%s,%s>" % (dims[0], dims[1], geo.group(1)) if len(dims) >= 2 else "gemm<%s>" % geo.group(1)
         v = float(row["Metric Value"].replace(",", ""))
         unit = row["Metric Unit"]
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
