@@ -597,7 +597,7 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
     const bool overlap = want_trtri && want_lauum && ovl_env && s == p->ex.main;
     if (want_trtri) {
       NvtxRange r("gpb:trtri(dist)");
-      int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), s, !overlap), "trtri_dist");
+      int rc = dist_rc(gpb::run_trtri_dist(dm, p->h_desc0, *p->dist, (double*)(p->ws + p->off_stage[0]), p->ex, !overlap), "trtri_dist");
       if (rc) return rc;
       if (!overlap) CU(gpb::run_alpha(dm, 1, p->n_max, s), "alpha");
     }

@@ -329,6 +329,44 @@ __global__ void __launch_bounds__(256) panel_copy_kernel(double* __restrict__ A,
   }
 }
 
+// The same copy for the 1 x Q path (tile t of panel k <-> slot t), 32 columns of a tile per CTA and 16-byte accesses for
+// full tiles: the pack and the unpack sit on the factorisation's critical chain between the panel and the update of the
+// next owner (8 GPUs, n = 32768: 120 + 110 us per 66 MB outer panel with the kernel above, a sixth of the chain).
+__global__ void __launch_bounds__(256) panel_copy2_kernel(double* __restrict__ A, long long ld, int nrows, int k,
+                                                          double* __restrict__ stage, int mode) {
+  const int I = k + blockIdx.x;
+  const int c0 = blockIdx.y * 32;
+  double* st = stage + (size_t)blockIdx.x * TILE_ELEMS + (size_t)c0 * GPB_NB;
+  const int rows = min(GPB_NB, nrows - I * GPB_NB);
+  const int cols = min(GPB_NB, nrows - k * GPB_NB) - c0;
+  double* a = A + (size_t)I * GPB_NB + (size_t)(k * GPB_NB + c0) * ld;
+  if (rows == GPB_NB && cols >= 32 && (ld & 1) == 0) {
+    double2 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q, i2 = idx & 63, c = idx >> 6;      // 64 double2 per column, 32 columns
+      v[q] = mode == 0 ? *reinterpret_cast<const double2*>(a + 2 * i2 + (size_t)c * ld)
+                       : *reinterpret_cast<const double2*>(st + 2 * i2 + c * GPB_NB);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = threadIdx.x + 256 * q, i2 = idx & 63, c = idx >> 6;
+      if (mode == 0) *reinterpret_cast<double2*>(st + 2 * i2 + c * GPB_NB) = v[q];
+      else *reinterpret_cast<double2*>(a + 2 * i2 + (size_t)c * ld) = v[q];
+    }
+    return;
+  }
+  for (int idx = threadIdx.x; idx < 32 * GPB_NB; idx += 256) {
+    const int i = idx & (GPB_NB - 1), c = idx >> 7;
+    if (i < rows && c < cols) {
+      if (mode == 0) st[idx] = a[i + (size_t)c * ld];
+      else a[i + (size_t)c * ld] = st[idx];
+    } else if (mode == 0) {
+      st[idx] = 0.0;
+    }
+  }
+}
+
 // plain copy of 128 x 128 doubles (inverse of the diagonal block in / out of the staging buffer)
 __global__ void __launch_bounds__(256) tile_copy_kernel(double* __restrict__ dst, const double* __restrict__ src) {
   for (int idx = threadIdx.x + blockIdx.x * 256; idx < TILE_ELEMS; idx += 256 * gridDim.x) dst[idx] = src[idx];
@@ -610,7 +648,7 @@ cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, 
 // the critical stream (A), of group s+2 on the medium-priority stream (B) and the rest on the low-priority one (C);
 // A(s) waits for B(s-1), B(s) for C(s-1), so the owner of group s+1 starts factorising while bulk updates still run.
 // ---------------------------------------------------------------------------------------------------------------
-static int post_gate() {      // 0: off, 1: receivers only (default), 2: receivers and the sender
+static int post_gate() {      // GPB_DIST_GATE=0 switches the receivers' gate off
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPB_DIST_GATE"); v = e ? atoi(e) : 1; }
   return v;
@@ -650,32 +688,30 @@ cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx
     for (int j = 0; j < kb; ++j) off[j + 1] = off[j] + (size_t)(nbr - (k0 + j) + 1) * TILE_ELEMS;
     if (mine) {
       for (int j = 0; j < kb; ++j) {
-        const int k = k0 + j;
+        const int k = k0 + j, nt = nbr - k;
         if (j > 0) GPB_CK(syrk(k0, j, k, k + 1, cs, "strip"));     // column k <- the j panels of the group before it
         GPB_CK(run_diag(dm, 1, k, cs));
         if ((k + 1) * GPB_NB <= n) {                               // full pivot block: a panel exists below it
           const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
           GPB_CK((launch_geo<Cfg>(GeoDistPanel{dm, k, 1, 0}, dim3(Tm, 1, 1), cs, false, "panel", k)));
         }
-      }
-      GPB_CK(cudaEventRecord(ex.ev_p[e], cs));
-      GPB_CK(cudaStreamWaitEvent(xs, ex.ev_p[e], 0));
-      if (s >= 2 && post_gate() >= 2) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_d[e], 0));   // see the receivers' gate below
-      TraceSpan span("pack", xs, k0, kb);
-      for (int j = 0; j < kb; ++j) {
-        const int k = k0 + j, nt = nbr - k;
-        panel_copy_kernel<<<nt, 256, 0, xs>>>(h.A, (long long)ld, nrows, k, 0, st + off[j], map, 0, q, q, 0);
+        // block column k is final: it is packed on the communication stream while the next column of the group is
+        // being factorised (ev_p is re-recorded per column; the wait is enqueued right behind each record)
+        GPB_CK(cudaEventRecord(ex.ev_p[e], cs));
+        GPB_CK(cudaStreamWaitEvent(xs, ex.ev_p[e], 0));
+        TraceSpan span("pack", xs, k, nt);
+        panel_copy2_kernel<<<dim3(nt, 4), 256, 0, xs>>>(h.A, (long long)ld, nrows, k, st + off[j], 0);
         tile_copy_kernel<<<8, 256, 0, xs>>>(st + off[j] + (size_t)nt * TILE_ELEMS, h.Wd + (size_t)k * TILE_ELEMS);
         g_launches += 2;
+        GPB_CK(cudaGetLastError());
       }
-      GPB_CK(cudaGetLastError());
     }
     // A receiver posts its side of the broadcast only when its own bulk update of step s-2 has finished: that is when
     // the owner of this group could start factorising it (its A(s-1) waits for B(s-2), which waits for C(s-3)), give or
     // take one step of load balance.  Posted earlier, the NCCL kernel spins for the owner's data for milliseconds and
     // its CTAs (whole register files) take 16 - 24 SMs away from the bulk update (launch timeline on 2 GPUs,
     // n = 32768: receive spans of 4 - 5 ms per outer step, bulk update at 24 instead of 31 TFLOP/s).  GPB_DIST_GATE=0: off.
-    // Gating the sender the same way (GPB_DIST_GATE=2) measured slightly worse (2 GPUs: potrf 213.5 vs 210.4 ms).
+    // Gating the sender the same way measured slightly worse (2 GPUs: potrf 213.5 vs 210.4 ms).
     if (s >= 2 && !mine && post_gate() >= 1) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_d[e], 0));
     {
       TraceSpan span("bcast", xs, k0, kb);
@@ -685,7 +721,7 @@ cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx
       TraceSpan span("unpack", xs, k0, kb);
       for (int j = 0; j < kb; ++j) {
         const int k = k0 + j, nt = nbr - k;
-        panel_copy_kernel<<<nt, 256, 0, xs>>>(h.A, (long long)ld, nrows, k, 0, st + off[j], map, 0, owner, q, 1);
+        panel_copy2_kernel<<<dim3(nt, 4), 256, 0, xs>>>(h.A, (long long)ld, nrows, k, st + off[j], 1);
         tile_copy_kernel<<<8, 256, 0, xs>>>(h.Wd + (size_t)k * TILE_ELEMS, st + off[j] + (size_t)nt * TILE_ELEMS);
         g_launches += 2;
       }
@@ -835,43 +871,63 @@ static int own_cols_upto(int J_incl, int world, int rank) {   // own block colum
   return J_incl < rank ? 0 : (J_incl - rank) / world + 1;
 }
 
-cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s, bool exchange) {
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, const Exec& ex, bool exchange) {
   using Cfg = CfgHalf;
   const int n = h.n, world = D.world, rank = D.rank;
   const int nblk = (n + GPB_NB - 1) / GPB_NB;
   const size_t ld = h.ld;
+  cudaStream_t s = ex.main, cs = ex.crit, ss = ex.side;
   // zero the own block columns of X (the accumulation starts from 0; rows above the diagonal block stay 0 = W's zeros)
   for (int J = rank; J < nblk; J += world) {
     const int cols = std::min(GPB_NB, n - J * GPB_NB);
     GPB_CK(cudaMemsetAsync(h.Kinv + (size_t)J * GPB_NB * ld, 0, (size_t)cols * ld * sizeof(double), s));
   }
+  GPB_CK(cudaEventRecord(ex.ev_fork, s));
+  GPB_CK(cudaStreamWaitEvent(cs, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
   auto diag_solve = [&](int I) -> cudaError_t {            // X[I, J] <- -Wd_I X[I, J] (own J < I), X[I, I] <- Wd_I
     const int nJ_lt = own_cols_upto(I - 1, world, rank);
     const int nJ_le = own_cols_upto(I, world, rank);
     if (nJ_le == 0) return cudaSuccess;
-    if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), s, "tri_diag", I)));
-    tri_diag_store_kernel<<<nJ_le, 256, 0, s>>>(dm, scratch, I, world, rank);
+    if (nJ_lt > 0) GPB_CK((launch_geo2<Cfg, false, true>(GeoDistTriDiag{dm, scratch, I, world, rank}, dim3(GPB_NB / Cfg::BM, nJ_lt, 1), cs, "tri_diag", I)));
+    tri_diag_store_kernel<<<nJ_le, 256, 0, cs>>>(dm, scratch, I, world, rank);
     ++g_launches;
     return cudaGetLastError();
   };
-  auto update = [&](int I, int kb, int row_lo, int row_hi) -> cudaError_t {
+  auto update = [&](int I, int kb, int row_lo, int row_hi, cudaStream_t st, const char* tag) -> cudaError_t {
     const int nJ = own_cols_upto(I + kb - 1, world, rank);
     if (nJ == 0 || row_hi <= row_lo) return cudaSuccess;
     return launch_geo2<Cfg, false, true>(GeoDistTriUpdate{dm, I, kb, row_lo, row_hi, world, rank},
-                                         dim3((row_hi - row_lo + Cfg::BM - 1) / Cfg::BM, nJ, 1), s, "tri_upd", I);
+                                         dim3((row_hi - row_lo + Cfg::BM - 1) / Cfg::BM, nJ, 1), st, tag, I);
   };
+  // Look-ahead: the block rows of the NEXT outer step receive this step's update on the critical stream, right behind
+  // the two small triangular products, so that the next step's products run while the rest of the update (all remaining
+  // rows, low-priority stream) is still in flight.  A row receives the updates of the outer steps in order: the "next"
+  // update of step t waits for the rest-update of step t-1 (ev_d), the rest-updates follow each other on their stream.
   const bool wide = potrf_outer_blocks(n) > 1;             // two block rows per far update (k = 256), as in the factorisation
-  for (int I = 0; I < nblk;) {
+  int step = 0;
+  for (int I = 0; I < nblk; ++step) {
     GPB_CK(diag_solve(I));
     int kb = 1;
     if (wide && (I + 2) * GPB_NB <= n) {
-      GPB_CK(update(I, 1, (I + 1) * GPB_NB, (I + 2) * GPB_NB));   // strip: block row I+1
+      GPB_CK(update(I, 1, (I + 1) * GPB_NB, (I + 2) * GPB_NB, cs, "tri_strip"));   // strip: block row I+1
       GPB_CK(diag_solve(I + 1));
       kb = 2;
     }
-    GPB_CK(update(I, kb, (I + kb) * GPB_NB, n));
+    const int e = step & 1;
+    GPB_CK(cudaEventRecord(ex.ev_e[e], cs));
+    const int r1 = (I + kb) * GPB_NB, r2 = std::min(n, (I + kb + (wide ? 2 : 1)) * GPB_NB);
+    if (step > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_d[(step - 1) & 1], 0));
+    GPB_CK(update(I, kb, r1, r2, cs, "tri_next"));
+    GPB_CK(cudaStreamWaitEvent(ss, ex.ev_e[e], 0));
+    GPB_CK(update(I, kb, r2, n, ss, "tri_upd"));
+    GPB_CK(cudaEventRecord(ex.ev_d[e], ss));
     I += kb;
   }
+  GPB_CK(cudaEventRecord(ex.ev_join[0], cs));
+  GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
+  GPB_CK(cudaStreamWaitEvent(s, ex.ev_join[0], 0));
+  GPB_CK(cudaStreamWaitEvent(s, ex.ev_join[1], 0));
   if (!exchange) return cudaSuccess;   // run_exchange_lauum_dist ships W chunk by chunk under the W^T W product
   // exchange: block column J of W from its owner's Kinv into everybody's A (whole columns: contiguous, in place)
   for (int J0 = 0; J0 < nblk; J0 += 64) {
@@ -905,9 +961,11 @@ cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const Dis
   const int n = h.n, world = D.world, rank = D.rank;
   const int nblk = (n + GPB_NB - 1) / GPB_NB;
   const size_t ld = h.ld;
-  cudaStream_t s = ex.main, xs = ex.comm;
-  GPB_CK(cudaEventRecord(ex.ev_fork, s));
+  cudaStream_t xs = ex.comm, cs2[2] = {ex.mid, ex.side};
+  GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
   GPB_CK(cudaStreamWaitEvent(xs, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(cs2[0], ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(cs2[1], ex.ev_fork, 0));
   int chunk = (nblk + 7) / 8;                              // 8 chunks, at least 8 block columns each
   if (chunk < 8) chunk = 8;
   int c = 0;
@@ -922,6 +980,9 @@ cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const Dis
       }
       GPB_TR(D.tr->group_end());
     }
+    // the products of consecutive chunks go to two streams: a chunk's last, partially filled wave of long tiles (up to
+    // n deep) overlaps with the next chunk's first tiles instead of idling the machine once per chunk
+    cudaStream_t s = cs2[c & 1];
     GPB_CK(cudaEventRecord(ex.ev_x[c & 1], xs));
     GPB_CK(cudaStreamWaitEvent(s, ex.ev_x[c & 1], 0));
     const int nJ = own_cols_upto(J1 - 1, world, rank);     // own block columns J <= the last row block of the chunk
@@ -929,6 +990,12 @@ cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const Dis
       GPB_CK((launch_geo2<Cfg, true, true>(GeoDistLauum{dm, world, rank, J0 * GPB_NB, J1 * GPB_NB},
                                            dim3((J1 - J0) * GPB_NB / Cfg::BM, nJ, 1), s, "lauum", J0)));
   }
+  GPB_CK(cudaEventRecord(ex.ev_join[3], cs2[0]));
+  GPB_CK(cudaEventRecord(ex.ev_join[1], cs2[1]));
+  GPB_CK(cudaEventRecord(ex.ev_join_comm, xs));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[3], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join_comm, 0));
   return cudaSuccess;
 }
 

@@ -39,7 +39,7 @@ size_t dist_stage_bytes(int n);
 int dist_owned_cols(int J_lo, int J_hi, int Q, int q, int OW, int* cols, int cap);   // own block columns in [J_lo, J_hi)
 cudaError_t run_potrf_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* const stage[2], const Exec& ex);
 // exchange = false leaves W = inv(L) split by block column in Kinv (run_exchange_lauum_dist must follow)
-cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, cudaStream_t s, bool exchange);
+cudaError_t run_trtri_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, double* scratch, const Exec& ex, bool exchange);
 cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, const Exec& ex);
 cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, cudaStream_t s);
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s);
