@@ -429,7 +429,11 @@ def run_dist(ctx, key, steps, warmup):
         "roofline": {"bound": "tensor", "kernel": "Cholesky factorisation stage (gemm_kernel<GeoSyrk> trailing updates, "
                      "panel products, diagonal blocks; %d GPU%s)" % (world, "" if world == 1 else "s"),
                      "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                     "traffic": None, "traffic_note": "not measured in this run (tensor-bound stage)",
+                     "traffic": _traffic(key + "_syrk_bulk_first") if world == 1 else None,
+                     "traffic_note": ("static: ncu capture under profiles/ of the stage's LARGEST launch (first bulk trailing "
+                                      "update, k = 1024, 26.5 ms), DRAM bytes per launch; algorithmic bytes of that launch "
+                                      "8.3e9 (RED read-modify-write of the lower trailing matrix + the panel)"
+                                      if world == 1 else "not measured (tensor-bound stage)"),
                      "flops_per_stage": n ** 3 / 3.0, "stage_ms": stage_ms["potrf"],
                      "peak_source": "measured live on rank 0: DMMA.8x8x4 register-operand probe (gpb_microbench) x n_gpus; "
                                     "MEASURED_PEAKS.json has no FP64 entry"},

@@ -38,6 +38,7 @@ __device__ __forceinline__ bool carried_row_separate(const GpbMat& d, int sep) {
 struct GeoSyrk {
   const GpbMat* mats;
   int kp, kb, c_lo, c_hi, sep;
+  int grp = 0;   // bulk launches that reach the last tile column: super-tile raster (groups of 8 tile columns)
   template <int BM, int BN>
   __device__ bool tile(TileJob& J, const dim3& b) const {
     const GpbMat& d = mats[b.z];
@@ -46,7 +47,15 @@ struct GeoSyrk {
     if (r0 >= nrows || r0 > d.n) return false;   // every block of the panel must be a full pivot block
     const int Tm = (nrows - r0 + BM - 1) / BM;
     int ti, tj;
-    if (!tri_map(b.x, Tm, BN / BM, c_lo, c_hi, ti, tj)) return false;
+    constexpr int R = BN / BM;
+    if (grp && c_hi >= (Tm + R - 1) / R) {
+      // The tile columns [c_lo, end) form a lower triangle of their own (rows shifted by R c_lo).  In column-sweep order
+      // a wave of 592 tiles streams 590 different A slabs (k = 1024: 0.5 MB each, more than the 126 MB L2) and the next
+      // column re-reads them from DRAM: ncu at n = 32768, first bulk update: 31 GB per launch, L2 hit rate 62 %
+      // (profiles/r2e_ncu_syrk_bulk_k1024_n32768.txt).  Groups of 8 columns x ~74 row tiles keep a wave's operands in L2.
+      if (!tri_map_grouped(b.x, Tm - R * c_lo, R, 8, ti, tj)) return false;
+      ti += R * c_lo; tj += c_lo;
+    } else if (!tri_map(b.x, Tm, R, c_lo, c_hi, ti, tj)) return false;
     const size_t ld = d.ld;
     const double* P = d.A + (size_t)kp * GPB_NB * ld;
     J.A = P + r0 + ti * BM;
@@ -1022,6 +1031,12 @@ cudaError_t linalg_init() {
   return cudaSuccess;
 }
 
+static bool grouped_raster() {      // GPB_SYRK_GROUPED=0: column-sweep tile order in the bulk updates
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPB_SYRK_GROUPED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static bool quarter_tiles() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPB_QUARTER"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1268,7 +1283,7 @@ static cudaError_t potrf_impl(const GpbMat* dm, int B, int n_max, int aug, bool 
                                                    dim3((unsigned)tri_count(Tq, 4, c_lo, c_hi), 1, B), st, false, tag, kp)));
     } else {
       const int Tm = (rows + BM - 1) / BM;
-      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep},
+      GPB_CK((launch_cfg<Cfg, false, false>(GeoSyrk{dm, kp, kb, c_lo, c_hi, sep, (bulk && grouped_raster()) ? 1 : 0},
                                             dim3((unsigned)tri_count(Tm, R, c_lo, c_hi), 1, B), st, bulk, tag, kp)));
     }
     return carried(kp, kb, c_lo, c_hi, 1, st);
