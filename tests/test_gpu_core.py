@@ -294,10 +294,15 @@ def test_large_roundtrip_properties():
     assert float(r2.abs().max()) <= 1e-6 * float(v.abs().max())
 
 
-def test_wide_outer_panels_on_ragged_batches_subprocess():
-    """The 256-wide outer panels of the Cholesky driver are chosen for n >= 6144 only; GPB_POTRF_KB=2 (read once per
-    process) forces them, so a subprocess evaluates a ragged batch - sizes on both sides of block boundaries, odd and
-    even numbers of blocks - against the oracle with the wide panels on."""
+@pytest.mark.parametrize("env_extra", [{"GPB_POTRF_KB": "2"}, {"GPB_POTRF_KB": "3"}, {"GPB_POTRF_KB": "4"},
+                                       {"GPB_POTRF_KB": "8"},
+                                       {"GPB_POTRF_T2": "384", "GPB_POTRF_T4": "1024", "GPB_POTRF_T8": "1664"}])
+def test_wide_outer_panels_on_ragged_batches_subprocess(env_extra):
+    """The outer panels of the Cholesky driver are 128 W wide with W chosen per outer step from the remaining rows
+    (8 / 4 / 2 / 1 from 20480 / 10240 / 5120 rows; batches: 4 from n = 1024).  GPB_POTRF_KB (read once per process) forces
+    one width, GPB_POTRF_T2/_T4/_T8 move the thresholds so that a 2300-point GP walks through all four widths; a
+    subprocess evaluates a ragged batch - sizes on both sides of block boundaries, odd and even numbers of blocks - and
+    single GPs on the look-ahead path against the oracle."""
     import subprocess
     import sys
     script = r"""
@@ -323,9 +328,21 @@ for b, n in enumerate(ns):
     assert abs(nll[b] - want) <= 1e-10 * abs(want), (n, nll[b], want)
     gw = np.concatenate([np.asarray(t).reshape(-1) for t in g] + [[gn]])
     assert np.max(np.abs(grads[b] - gw)) <= 1e-8 * np.max(np.abs(gw)), (n, grads[b], gw)
+# one GP per plan: the look-ahead driver (depth 2, three priority levels) with the same widths
+for n in (1153, 2300, 1536):
+    rng = np.random.default_rng(90 + n)
+    x = np.sort(rng.uniform(0, 1, (n, 1)), axis=0); y = np.sin(7 * x) + 0.1 * rng.standard_normal((n, 1))
+    single = eng.Plan([prog], [n], want_grad=True)
+    single.set_data(0, torch.tensor(x), torch.tensor(y)); single.set_hp(0, hp, 1e-2)
+    single.eval(eng.STAGES_LML_GRAD); torch.cuda.synchronize()
+    nll1, g1, info1 = single.results()
+    want, g, gn = orc.nll_and_grad(tree, [np.asarray(v) for v in hp], 1e-2, x, y, reference_distance=False)
+    gw = np.concatenate([np.asarray(t).reshape(-1) for t in g] + [[gn]])
+    assert int(info1[0]) == 0 and abs(nll1[0] - want) <= 1e-10 * abs(want), (n, nll1[0], want)
+    assert np.max(np.abs(g1[0] - gw)) <= 1e-8 * np.max(np.abs(gw)), (n, g1[0], gw)
 print("ok")
 """ % ROOT
-    env = dict(os.environ, GPB_POTRF_KB="2")
+    env = dict(os.environ, **env_extra)
     out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
