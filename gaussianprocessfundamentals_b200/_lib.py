@@ -55,6 +55,7 @@ SIGNATURES = {
     "gpb_dist_loopback_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_pp]),
     "gpb_dist_destroy": (None, [ctypes.c_void_p]),
     "gpb_plan_create_dist": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, c_void_pp]),
+    "gpb_plan_create_dist_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, c_void_pp]),
     "gpb_dist_owner": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "gpb_dist_col_width": (ctypes.c_int, [ctypes.c_int]),
     "gpb_dist_owner_w": (ctypes.c_int, [ctypes.c_int] * 5),

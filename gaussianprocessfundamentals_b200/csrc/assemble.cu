@@ -27,6 +27,7 @@ struct AsmArgs {
   int lower_only;
   const double* y; int aug;   // aug: row n receives y^T, (n,n) receives 0
   int own_P, own_Q, own_p, own_q, own_W;   // distributed plans: write only the 128-blocks this process owns (own_P == 0: all)
+  int own_compact;                         // column storage: K holds only the own block columns (device_abi.cuh)
 };
 
 __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, int T) {
@@ -69,20 +70,21 @@ __device__ __forceinline__ void assemble_tile(const AsmArgs& a, int ti, int tj, 
       p.xj = s_xj + c * a.dim; p.gj = gj;
       double v = gpb_eval(s_code, a.n_ops, p);
       if (!a.X2 && gi == gj) v += noise;
-      a.K[gi + gj * a.ld] = v;
+      a.K[gi + (a.own_compact ? gpb_local_col(gj, a.own_Q, a.own_q, a.own_W) : gj) * a.ld] = v;
     }
   }
   if (own_aug) {
     // carried right-hand side: row n of the factorisation workspace
     if (tid < A_T) {
       const long long gj = j0 + tid;
-      if (gj < a.n) a.K[a.n + gj * a.ld] = a.y[gj];
+      if (gj < a.n) a.K[a.n + (a.own_compact ? gpb_local_col(gj, a.own_Q, a.own_q, a.own_W) : gj) * a.ld] = a.y[gj];
     }
   }
   if (a.aug && ti == T - 1 && tj == T - 1 && tid == 0) {
     // element (n, n) accumulates -z^T z; in a distributed plan it belongs to block (n / 128, n / 128)
     const int bn = (int)(a.n / GPB_NB);
-    if (!a.own_P || (bn % a.own_P == a.own_p && (bn / a.own_W) % a.own_Q == a.own_q)) a.K[a.n + a.n * a.ld] = 0.0;
+    if (!a.own_P || (bn % a.own_P == a.own_p && (bn / a.own_W) % a.own_Q == a.own_q))
+      a.K[a.n + (a.own_compact ? gpb_local_col(a.n, a.own_Q, a.own_q, a.own_W) : a.n) * a.ld] = 0.0;
   }
 }
 
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) assemble_batched_kernel(const GpbMat* __r
   a.X = d.X; a.X2 = nullptr; a.n = d.n; a.m = d.n; a.hp = d.hp; a.n_hp = d.n_hp; a.noise = d.noise;
   a.K = d.A; a.ld = d.ld; a.lower_only = 1; a.y = d.y; a.aug = d.aug;
   a.own_P = d.own_P; a.own_Q = d.own_Q; a.own_p = d.own_p; a.own_q = d.own_q; a.own_W = d.own_W;
+  a.own_compact = d.own_compact;
   assemble_tile(a, ti, tj, T);
 }
 
@@ -249,7 +252,7 @@ cudaError_t run_assemble_rect(const int32_t* code_dev, int n_ops, int dim, int c
   a.code = code_dev; a.n_ops = n_ops; a.dim = dim; a.cp_mode = cp_mode;
   a.X = X; a.X2 = X2; a.n = n; a.m = m; a.hp = hp_dev; a.n_hp = n_hp; a.noise = noise_dev;
   a.K = K; a.ld = ldk; a.lower_only = lower_only; a.y = nullptr; a.aug = 0;
-  a.own_P = a.own_Q = a.own_p = a.own_q = 0; a.own_W = 1;
+  a.own_P = a.own_Q = a.own_p = a.own_q = 0; a.own_W = 1; a.own_compact = 0;
   const int Tm = (int)((n + A_T - 1) / A_T), Tn = (int)((m + A_T - 1) / A_T);
   if (Tm == 0 || Tn == 0) return cudaSuccess;
   const size_t smem = asm_smem_bytes(n_ops, n_hp, dim);

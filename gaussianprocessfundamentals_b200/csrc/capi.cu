@@ -188,6 +188,9 @@ struct gpb_plan {
   int n_graphs, graphs_off;
   gpb::DistCtx* dist;       // non-null: ONE GP factorised over a process grid (dist.cu)
   size_t off_stage[2];      // panel staging buffers of a distributed plan
+  int col_storage;          // distributed plan that keeps only the own block columns (likelihood only; dist.cu)
+  size_t off_ring[3], off_gdesc;   // column storage: ring of outer-panel buffers, descriptors of the own column groups
+  int n_own_groups;
   GpbMat h_desc0;           // host copy of the first descriptor (distributed plans)
   std::vector<GpbMat> h_desc;   // host copy of all descriptors
 };
@@ -334,7 +337,7 @@ int gpb_assemble(const gpb_program_t* prog, const double* X, const double* X2, i
 }
 
 static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb::DistCtx* dist,
-                       gpb_plan_t** out) {
+                       gpb_plan_t** out, int col_storage = 0) {
   if (B <= 0) return fail_arg(1, "B <= 0");
   if (!progs) return fail_arg(2, "progs is null");
   if (!n) return fail_arg(3, "n is null");
@@ -344,6 +347,8 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
   gpb_plan* p = new gpb_plan;
   p->B = B; p->want_grad = want_grad ? 1 : 0; p->ws = nullptr; p->dist = dist;
   p->off_stage[0] = p->off_stage[1] = 0;
+  p->col_storage = col_storage; p->off_gdesc = 0; p->n_own_groups = 0;
+  p->off_ring[0] = p->off_ring[1] = p->off_ring[2] = 0;
   p->n_max = 0; p->n_hp_max = 0; p->n_ops_max = 0; p->dim = progs[0] ? progs[0]->dim : 1;
   p->mats.resize(B); p->progs.assign(progs, progs + B);
   p->hp_prefix.resize(B + 1); p->grad_prefix.resize(B + 1);
@@ -397,7 +402,14 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     m.off_part = off; off = al(off + (size_t)m.nblk * 8);
     m.off_wd = off; off = al(off + (size_t)m.nblk * GPB_NB * GPB_NB * 8);
     m.off_gpart = off; off = al(off + (want_grad ? (size_t)m.n_gtiles * (g->n_hp + 1) * 8 : 0));
-    put(GPB_BUF_A, (size_t)m.ld * (n[b] + 1) * 8);
+    if (col_storage) {
+      // only the own block columns (full 128-wide, packed) of the (n + 1)-column workspace
+      const int nbr = (int)((n[b] + 1 + GPB_NB - 1) / GPB_NB);
+      const int own = gpb_owned_cols_below(nbr, dist->Q, dist->q, dist->OW);
+      put(GPB_BUF_A, (size_t)m.ld * ((size_t)own * GPB_NB + GPB_NB) * 8);
+    } else {
+      put(GPB_BUF_A, (size_t)m.ld * (n[b] + 1) * 8);
+    }
     put(GPB_BUF_KINV, want_grad ? (size_t)m.ld * n[b] * 8 : 0);
     m.off[GPB_BUF_HP] = p->off_hp_all + p->hp_prefix[b] * 8; m.bytes[GPB_BUF_HP] = (size_t)g->n_hp * 8;
     m.off[GPB_BUF_NOISE] = p->off_noise_all + (size_t)b * 8; m.bytes[GPB_BUF_NOISE] = 8;
@@ -406,7 +418,13 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     m.off[GPB_BUF_INFO] = p->off_info_all + (size_t)b * 4; m.bytes[GPB_BUF_INFO] = 4;
     m.off[GPB_BUF_TERMS] = p->off_terms_all + (size_t)b * 16; m.bytes[GPB_BUF_TERMS] = 16;
   }
-  if (dist) {
+  if (dist && col_storage) {
+    for (int i = 0; i < 3; ++i) { p->off_ring[i] = off; off = al(off + gpb::dist_ring_bytes((int)n[0], dist->OW)); }
+    const int nblk0 = (int)((n[0] + GPB_NB - 1) / GPB_NB);
+    const int ngroups = (nblk0 + dist->OW - 1) / dist->OW;
+    p->n_own_groups = ngroups > dist->q ? (ngroups - dist->q + dist->Q - 1) / dist->Q : 0;
+    p->off_gdesc = off; off = al(off + (size_t)(p->n_own_groups + 1) * sizeof(GpbMat));
+  } else if (dist) {
     for (int i = 0; i < 2; ++i) { p->off_stage[i] = off; off = al(off + gpb::dist_stage_bytes((int)n[0])); }
   }
   for (int b = 0; b < B; ++b) {
@@ -444,6 +462,7 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_x[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_join_comm, cudaEventDisableTiming);
+  for (int i = 0; i < 9 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_ring[i / 3][i % 3], cudaEventDisableTiming);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ex.ev_join[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ex.ev_fork, cudaEventDisableTiming);
   p->n_graphs = 0; p->graphs_off = 0; p->gstream = nullptr;
@@ -462,6 +481,14 @@ static int plan_create(int B, const gpb_program_t* const* progs, const int64_t* 
 
 int gpb_plan_create(int B, const gpb_program_t* const* progs, const int64_t* n, int want_grad, gpb_plan_t** out) {
   return plan_create(B, progs, n, want_grad, nullptr, out);
+}
+
+int gpb_plan_create_dist_columns(const gpb_program_t* prog, int64_t n, gpb_dist_t* dist, gpb_plan_t** out) {
+  if (!prog) return fail_arg(1, "prog is null");
+  if (!dist || !dist->ctx) return fail_arg(3, "dist is null");
+  if (dist->ctx->P != 1) return fail_arg(3, "column storage needs a 1 x Q grid");
+  const gpb_program_t* progs[1] = {prog};
+  return plan_create(1, progs, &n, 0, dist->ctx, out, 1);
 }
 
 int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out) {
@@ -510,7 +537,21 @@ int gpb_plan_bind(gpb_plan_t* p, void* workspace) {
     if (p->dist) {
       d.own_P = p->dist->P; d.own_Q = p->dist->Q; d.own_p = p->dist->p; d.own_q = p->dist->q; d.own_W = p->dist->OW;
       d.col_world = p->dist->world; d.col_rank = p->dist->rank;
+      d.own_compact = p->col_storage;
     }
+  }
+  if (p->col_storage) {
+    // one descriptor per own group of block columns: A shifted so that d.A + k * 128 * ld (what the diagonal-block kernel
+    // and the panel product compute for block column k) lands on the group's packed columns
+    std::vector<GpbMat> gd(p->n_own_groups + 1, h[0]);
+    const int OW = p->dist->OW, Q = p->dist->Q, q = p->dist->q;
+    for (int g = 0; g < p->n_own_groups; ++g) {
+      const long long k0 = (long long)(g * Q + q) * OW, t0 = (long long)g * OW;
+      gd[g].A = h[0].A + (t0 - k0) * (long long)GPB_NB * h[0].ld;
+      gd[g].own_compact = 0;
+    }
+    cudaError_t ge = cudaMemcpy(p->ws + p->off_gdesc, gd.data(), gd.size() * sizeof(GpbMat), cudaMemcpyHostToDevice);
+    if (ge != cudaSuccess) return fail_cuda(ge, "bind (group descriptors)");
   }
   p->h_desc0 = h[0];
   p->h_desc = h;
@@ -562,6 +603,8 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
   if (!p->ws) return fail_arg(1, "plan is not bound");
   if ((stages & (GPB_STAGE_INVERSE | GPB_STAGE_TRTRI | GPB_STAGE_LAUUM | GPB_STAGE_GRAD)) && !p->want_grad)
     return fail_arg(2, "plan was created without gradient workspace");
+  if (p->col_storage && (stages & ~(GPB_STAGE_ASSEMBLE | GPB_STAGE_POTRF | GPB_STAGE_NLL)))
+    return fail_arg(2, "a column-storage plan evaluates the likelihood only (ASSEMBLE | POTRF | NLL): the factor is not replicated");
   { const int rc_state = advance_state(p, stages); if (rc_state) return rc_state; }
   cudaStream_t s = (cudaStream_t)stream;
   const GpbMat* dm = (const GpbMat*)(p->ws + p->off_desc);
@@ -572,6 +615,25 @@ int gpb_plan_eval(gpb_plan_t* p, int stages, void* stream) {
       NvtxRange r("gpb:assemble");
       CU(cudaMemsetAsync(p->ws + p->off_info_all, 0, 4, s), "reset info");
       CU(plan_assemble(p, dm, s), "assemble");
+    }
+    if (p->col_storage) {
+      if (stages & GPB_STAGE_POTRF) {
+        NvtxRange r("gpb:potrf(dist, column storage)");
+        double* ring[3] = {(double*)(p->ws + p->off_ring[0]), (double*)(p->ws + p->off_ring[1]), (double*)(p->ws + p->off_ring[2])};
+        cudaError_t e = gpb::run_potrf_dist_store((const GpbMat*)(p->ws + p->off_gdesc), p->h_desc0, *p->dist, ring, p->ex);
+        if (e != cudaSuccess) {
+          if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }
+          return fail_cuda(e, "potrf_dist_store");
+        }
+      }
+      if (stages & GPB_STAGE_NLL) {
+        cudaError_t e = gpb::run_finalize_dist_store(dm, *p->dist, p->h_desc0.tmpv, std::log(M_PI * 2.0), s);
+        if (e != cudaSuccess) {
+          if (e == cudaErrorUnknown && gpb::dist_last_error()[0]) { g_err = gpb::dist_last_error(); return 2000; }
+          return fail_cuda(e, "finalize_dist_store");
+        }
+      }
+      return 0;
     }
     if (stages & GPB_STAGE_POTRF) {
       NvtxRange r("gpb:potrf(dist)");
@@ -784,6 +846,7 @@ void gpb_plan_destroy(gpb_plan_t* p) {
       cudaEventDestroy(p->ex.ev_p[i]); cudaEventDestroy(p->ex.ev_x[i]);
     }
     cudaEventDestroy(p->ex.ev_join_comm);
+    for (int i = 0; i < 9; ++i) cudaEventDestroy(p->ex.ev_ring[i / 3][i % 3]);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ex.ev_join[i]);
     cudaEventDestroy(p->ex.ev_fork);
     for (int i = 0; i < p->n_graphs; ++i) cudaGraphExecDestroy(p->graph_exec[i]);

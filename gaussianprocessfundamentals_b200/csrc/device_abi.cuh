@@ -41,9 +41,25 @@ struct GpbMat {
   // distributed plans (dist.cu): block (I, J) of 128 x 128 is owned by process (I mod own_P, (J / own_W) mod own_Q) -
   // block columns are dealt out in groups of own_W (the outer panel of the factorisation); own_P == 0: all
   int own_P, own_Q, own_p, own_q, own_W;
+  // own_compact != 0 (column storage, 1 x Q grids): A holds ONLY the block columns this process owns, packed in ascending
+  // order - global column j lives in local column gpb_local_col(j) - instead of the full (n + 1) x ld matrix
+  int own_compact;
   // gradient stages of a distributed plan: block column J belongs to rank J mod col_world (col_world == 0: all)
   int col_world, col_rank;
 };
+
+// Block columns owned by process column q when they are dealt out in groups of W over Q process columns: how many of
+// them lie below block column J, and the t-th one (ascending).
+__host__ __device__ inline int gpb_owned_cols_below(int J, int Q, int q, int W) {
+  const int g = J / W, r = J % W;
+  const int groups = g > q ? (g - q + Q - 1) / Q : 0;       // owned groups q, q + Q, ... that end before group g
+  return groups * W + ((g % Q == q) ? r : 0);
+}
+__host__ __device__ inline int gpb_owned_col_at(int t, int Q, int q, int W) { return ((t / W) * Q + q) * W + t % W; }
+// local column (elements) of global column j of a column-storage plan; j must lie in an owned block column
+__host__ __device__ inline long long gpb_local_col(long long j, int Q, int q, int W) {
+  return (long long)gpb_owned_cols_below((int)(j / GPB_NB), Q, q, W) * GPB_NB + j % GPB_NB;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -396,13 +396,9 @@ struct GeoDistPanel {
   }
 };
 
-// block columns owned by process column q (groups of OW, dealt out cyclically over Q): how many lie below J, and the t-th
-__host__ __device__ inline int owned_cols_below(int J, int Q, int q, int OW) {
-  const int g = J / OW, r = J % OW;
-  const int groups = g > q ? (g - q + Q - 1) / Q : 0;       // owned groups q, q + Q, ... that end before group g
-  return groups * OW + ((g % Q == q) ? r : 0);
-}
-__host__ __device__ inline int owned_col_at(int t, int Q, int q, int OW) { return ((t / OW) * Q + q) * OW + t % OW; }
+// block columns owned by process column q (groups of OW, dealt out cyclically over Q): device_abi.cuh
+__host__ __device__ inline int owned_cols_below(int J, int Q, int q, int OW) { return gpb_owned_cols_below(J, Q, q, OW); }
+__host__ __device__ inline int owned_col_at(int t, int Q, int q, int OW) { return gpb_owned_col_at(t, Q, q, OW); }
 
 // trailing update with panel k of the blocks (I, J) this rank owns, J in [J_lo, J_hi):  A[I, J] -= L[I, k] L[J, k]^T.
 // grid.y enumerates this rank's block columns of the range, grid.x the BM-row tiles from the diagonal block down.
@@ -668,8 +664,6 @@ cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx
   GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
   GPB_CK(cudaStreamWaitEvent(xs, ex.ev_fork, 0));
   const size_t ld = h.ld;
-  PanelMap map;
-  map.P = 1; map.seg_base[0] = 0; map.seg_first[0] = 0;
   auto syrk = [&](int kp, int kb, int Jlo, int Jhi, cudaStream_t s, const char* tag) -> cudaError_t {
     if (Jhi > nbr) Jhi = nbr;
     const int nc = count_owned_cols(Jlo, Jhi, Q, q, OW);
@@ -752,6 +746,190 @@ cudaError_t run_potrf_dist_cols(const GpbMat* dm, const GpbMat& h, const DistCtx
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[3], 0));
   GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join_comm, 0));
   return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// COLUMN STORAGE (1 x Q grids, likelihood only): every rank keeps ONLY its own block columns (groups of OW, packed in
+// ascending order: n^2 * 8 / Q bytes instead of n^2 * 8) plus a ring of three outer-panel buffers.  Same schedule as
+// run_potrf_dist_cols, with three differences:
+//   * no pack / unpack: the columns of an outer panel are adjacent in the owner's storage, so the owner broadcasts them
+//     in place (whole columns, OW * 128 * ld doubles) straight into the receivers' ring slot; the updates read the panel
+//     from there (the owner: from its own columns);
+//   * the diagonal-block kernel, the panel product and the strip update address block column k as d.A + k * 128 * ld:
+//     they get a descriptor per own group whose A is shifted so that this expression lands in the packed storage;
+//   * nothing is replicated, so the log-determinant, z^T z and the first bad pivot are reduced over the ranks
+//     (run_finalize_dist_store); inverse and gradient stages need the replicated plan.
+// A ring slot is reused by the third-next outer step: its broadcast waits for the three updates (A, B, C) that read it.
+// ---------------------------------------------------------------------------------------------------------------
+struct GeoColSyrk {
+  const double* panel;      // element (row 0, first column of the outer panel); column-major, ld
+  double* Aloc;             // packed own block columns
+  int ld, nrows, kb, J_lo, J_hi, Q, q, OW;
+  template <int BM, int BN>
+  __device__ bool tile(TileJob& J, const dim3& b) const {
+    static_assert(BN == GPB_NB, "block columns are 128 wide");
+    const int t = owned_cols_below(J_lo, Q, q, OW) + (int)b.y;          // local index of the b.y-th own column >= J_lo
+    const int Jb = owned_col_at(t, Q, q, OW);
+    if (Jb >= J_hi) return false;
+    const int row = Jb * GPB_NB + (int)b.x * BM;
+    if (row >= nrows) return false;
+    J.A = panel + row;
+    J.B = panel + (size_t)Jb * GPB_NB;
+    J.C = Aloc + row + (size_t)t * GPB_NB * ld;
+    J.lda = J.ldb = J.ldc = ld;
+    J.mrem = min(BM, nrows - row);
+    J.nrem = min(BN, nrows - Jb * GPB_NB);
+    J.klo = 0; J.khi = kb * GPB_NB;
+    J.alpha = -1.0; J.beta = 1.0; J.red = g_red_epilogue;
+    return true;
+  }
+};
+
+size_t dist_ring_bytes(int n, int OW) {
+  const size_t ld = (size_t)((n + 1 + 7) / 8 * 8);
+  return (size_t)OW * GPB_NB * ld * sizeof(double);
+}
+
+cudaError_t run_potrf_dist_store(const GpbMat* gdesc, const GpbMat& h, const DistCtx& D, double* const ring[3], const Exec& ex) {
+  using Cfg = CfgHalf;
+  constexpr int BM = Cfg::BM;
+  const int n = h.n, nrows = h.n + h.aug;
+  const int nblk = (n + GPB_NB - 1) / GPB_NB;
+  const int nbr = (nrows + GPB_NB - 1) / GPB_NB;
+  const int Q = D.Q, q = D.q, OW = D.OW;
+  cudaStream_t cs = ex.crit, ms = ex.mid, ss = ex.side, xs = ex.comm;
+  GPB_CK(cudaEventRecord(ex.ev_fork, ex.main));
+  GPB_CK(cudaStreamWaitEvent(cs, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ms, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(ss, ex.ev_fork, 0));
+  GPB_CK(cudaStreamWaitEvent(xs, ex.ev_fork, 0));
+  const size_t ld = h.ld;
+  double* Aloc = h.A;
+  auto syrk = [&](const double* panel, int kb, int Jlo, int Jhi, cudaStream_t s, const char* tag, int k0) -> cudaError_t {
+    if (Jhi > nbr) Jhi = nbr;
+    const int nc = count_owned_cols(Jlo, Jhi, Q, q, OW);
+    if (nc == 0) return cudaSuccess;
+    const int Tm = (nrows - Jlo * GPB_NB + BM - 1) / BM;
+    return launch_geo<Cfg>(GeoColSyrk{panel, Aloc, (int)ld, nrows, kb, Jlo, Jhi, Q, q, OW}, dim3(Tm, nc, 1), s, true, tag, k0);
+  };
+  const int ngroups = (nblk + OW - 1) / OW;
+  for (int s = 0; s < ngroups; ++s) {
+    const int k0 = s * OW, kb = std::min(OW, nblk - k0), e = s & 1, slot = s % 3;
+    const int owner = s % Q;
+    const bool mine = (q == owner);
+    const int t0 = (s / Q) * OW;                           // local index of block column k0 on its owner
+    double* own_panel = Aloc + (size_t)t0 * GPB_NB * ld;
+    if (mine) {
+      const GpbMat* gd = gdesc + s / Q;                    // A shifted: gd->A + k * 128 * ld is block column k of this group
+      for (int j = 0; j < kb; ++j) {
+        const int k = k0 + j;
+        if (j > 0)                                         // column k <- the j panels of the group before it (all local)
+          GPB_CK((launch_geo<Cfg>(GeoDistSyrk{gd, k0, j, k, k + 1, 1, 1, 0, 0, 1},
+                                  dim3((nrows - k * GPB_NB + BM - 1) / BM, 1, 1), cs, true, "strip", k)));
+        GPB_CK(run_diag(gd, 1, k, cs));
+        if ((k + 1) * GPB_NB <= n) {
+          const int Tm = (nrows - (k + 1) * GPB_NB + BM - 1) / BM;
+          GPB_CK((launch_geo<Cfg>(GeoDistPanel{gd, k, 1, 0}, dim3(Tm, 1, 1), cs, false, "panel", k)));
+        }
+      }
+      GPB_CK(cudaEventRecord(ex.ev_p[e], cs));
+      GPB_CK(cudaStreamWaitEvent(xs, ex.ev_p[e], 0));
+    } else {
+      if (s >= 3) for (int u = 0; u < 3; ++u) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_ring[slot][u], 0));   // slot free again
+      if (s >= 2 && post_gate() >= 1) GPB_CK(cudaStreamWaitEvent(xs, ex.ev_d[e], 0));                    // see run_potrf_dist_cols
+    }
+    {
+      TraceSpan span("bcast", xs, k0, kb);
+      double* buf = mine ? own_panel : ring[slot];
+      GPB_TR(D.tr->broadcast(buf, buf, (size_t)kb * GPB_NB * ld, owner, xs));
+    }
+    GPB_CK(cudaEventRecord(ex.ev_x[e], xs));
+    const int J1 = k0 + kb;
+    if (J1 >= nbr) continue;
+    const double* panel = mine ? own_panel : ring[slot];
+    cudaEvent_t ready = mine ? ex.ev_p[e] : ex.ev_x[e];
+    if (!mine) GPB_CK(cudaStreamWaitEvent(cs, ready, 0));
+    if (s > 0) GPB_CK(cudaStreamWaitEvent(cs, ex.ev_b[(s - 1) & 1], 0));
+    GPB_CK(syrk(panel, kb, J1, J1 + OW, cs, "A", k0));
+    GPB_CK(cudaEventRecord(ex.ev_ring[slot][0], cs));
+    GPB_CK(cudaStreamWaitEvent(ms, ready, 0));
+    if (s > 0) GPB_CK(cudaStreamWaitEvent(ms, ex.ev_d[(s - 1) & 1], 0));
+    GPB_CK(syrk(panel, kb, J1 + OW, J1 + 2 * OW, ms, "B", k0));
+    GPB_CK(cudaEventRecord(ex.ev_b[e], ms));
+    GPB_CK(cudaEventRecord(ex.ev_ring[slot][1], ms));
+    GPB_CK(cudaStreamWaitEvent(ss, ready, 0));
+    GPB_CK(syrk(panel, kb, J1 + 2 * OW, nbr, ss, "bulk", k0));
+    GPB_CK(cudaEventRecord(ex.ev_d[e], ss));
+    GPB_CK(cudaEventRecord(ex.ev_ring[slot][2], ss));
+  }
+  GPB_CK(cudaEventRecord(ex.ev_join[0], cs));
+  GPB_CK(cudaEventRecord(ex.ev_join[1], ss));
+  GPB_CK(cudaEventRecord(ex.ev_join[3], ms));
+  GPB_CK(cudaEventRecord(ex.ev_join_comm, xs));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[0], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[1], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join[3], 0));
+  GPB_CK(cudaStreamWaitEvent(ex.main, ex.ev_join_comm, 0));
+  return cudaSuccess;
+}
+
+// column storage: partial log-determinant, z^T z and first bad pivot over the OWN pivot columns -> red[0], red[1],
+// red[2 + rank]; after the all-reduce (sum) every rank holds all partials and finishes the likelihood itself
+__global__ void __launch_bounds__(1024) store_partials_kernel(const GpbMat* __restrict__ mats, double* __restrict__ red, int world,
+                                                              int rank) {
+  __shared__ double s_ld[32], s_q[32];
+  __shared__ int s_bad[32];
+  const GpbMat d = mats[0];
+  const int n = d.n;
+  const size_t ld = d.ld;
+  double lsum = 0.0, qsum = 0.0;
+  int bad = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (((i / GPB_NB) / d.own_W) % d.own_Q != d.own_q) continue;
+    const size_t c = (size_t)gpb_local_col(i, d.own_Q, d.own_q, d.own_W);
+    const double lii = d.A[i + c * ld];
+    const double z = d.A[n + c * ld];
+    if (!(lii > 0.0)) bad = min(bad, i + 1);
+    lsum += log(lii);
+    qsum += z * z;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  lsum = warp_sum(lsum); qsum = warp_sum(qsum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+  if (lane == 0) { s_ld[warp] = lsum; s_q[warp] = qsum; s_bad[warp] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    int w = 0x7fffffff;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_ld[i]; b += s_q[i]; w = min(w, s_bad[i]); }
+    // a rank whose columns hold a bad pivot contributes NaN-free sums: the likelihood is NaN whenever info != 0
+    red[0] = (w == 0x7fffffff) ? a : 0.0;
+    red[1] = (w == 0x7fffffff) ? b : 0.0;
+    for (int r = 0; r < world; ++r) red[2 + r] = 0.0;
+    red[2 + rank] = (w == 0x7fffffff) ? 0.0 : (double)w;
+  }
+}
+__global__ void store_finish_kernel(const GpbMat* __restrict__ mats, const double* __restrict__ red, int world, double log2pi) {
+  const GpbMat d = mats[0];
+  int info = 0;
+  for (int r = 0; r < world; ++r) {
+    const int w = (int)red[2 + r];
+    if (w > 0 && (info == 0 || w < info)) info = w;
+  }
+  *d.info = info;
+  *d.nll = info ? nan("") : 0.5 * red[1] + red[0] + 0.5 * ((double)d.n * log2pi);
+  d.terms[0] = red[1]; d.terms[1] = red[0];
+}
+
+cudaError_t run_finalize_dist_store(const GpbMat* dm, const DistCtx& D, double* red, double log2pi, cudaStream_t s) {
+  store_partials_kernel<<<1, 1024, 0, s>>>(dm, red, D.world, D.rank);
+  ++g_launches;
+  GPB_CK(cudaGetLastError());
+  GPB_TR(D.tr->allreduce_sum(red, (size_t)(2 + D.world), s));
+  store_finish_kernel<<<1, 1, 0, s>>>(dm, red, D.world, log2pi);
+  ++g_launches;
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

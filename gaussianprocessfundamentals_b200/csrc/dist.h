@@ -44,5 +44,11 @@ cudaError_t run_exchange_lauum_dist(const GpbMat* dm, const GpbMat& h, const Dis
 cudaError_t run_lauum_dist(const GpbMat* dm, const GpbMat& h, const DistCtx& D, cudaStream_t s);
 cudaError_t run_grad_allreduce(double* grad, int count, const DistCtx& D, cudaStream_t s);
 cudaError_t run_finalize_dist(const GpbMat* dm, double log2pi, cudaStream_t s);
+// column storage (1 x Q grids, likelihood only): gdesc = one descriptor per own group of block columns with A shifted so
+// that the single-GPU kernels address the packed storage; ring = three outer-panel buffers of dist_ring_bytes each;
+// red = 2 + world doubles of scratch
+size_t dist_ring_bytes(int n, int OW);
+cudaError_t run_potrf_dist_store(const GpbMat* gdesc, const GpbMat& h, const DistCtx& D, double* const ring[3], const Exec& ex);
+cudaError_t run_finalize_dist_store(const GpbMat* dm, const DistCtx& D, double* red, double log2pi, cudaStream_t s);
 
 }  // namespace gpb

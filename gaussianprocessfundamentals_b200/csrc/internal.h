@@ -24,6 +24,7 @@ struct Exec {
   cudaEvent_t ev_d[2];     // bulk update of outer step s complete (recorded on side)
   cudaEvent_t ev_p[2];     // outer panel factorised on its owner (recorded on crit, waited on by comm)
   cudaEvent_t ev_x[2];     // outer panel available on this rank (recorded on comm)
+  cudaEvent_t ev_ring[3][3]; // column storage: the updates (crit / mid / side) that read ring slot i are done
   cudaEvent_t ev_join_comm;  // comm -> caller's stream
   cudaEvent_t ev_join[4];  // crit / side / inv / mid -> caller's stream
 };

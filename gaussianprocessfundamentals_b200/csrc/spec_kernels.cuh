@@ -69,7 +69,7 @@ __device__ __forceinline__ void assemble_spec_body(const GpbMat* __restrict__ ma
   const int gi = i0 + r;
   if (own_main && gi < n) {
     const double* xi = s_xi + r * P::DIM;
-    double* dst = d.A + gi + (size_t)j0 * ld;
+    double* dst = d.A + gi + (size_t)(d.own_compact ? gpb_local_col(j0, d.own_Q, d.own_q, d.own_W) : (long long)j0) * ld;
 #pragma unroll 1
     for (int q = 0; q < S_T / 4; ++q) {
       const int c = cg + 4 * q;
@@ -82,11 +82,12 @@ __device__ __forceinline__ void assemble_spec_body(const GpbMat* __restrict__ ma
   }
   if (own_aug && tid < S_T) {
     const int gj = j0 + tid;
-    if (gj < n) d.A[n + (size_t)gj * ld] = d.y[gj];
+    if (gj < n) d.A[n + (size_t)(d.own_compact ? gpb_local_col(gj, d.own_Q, d.own_q, d.own_W) : (long long)gj) * ld] = d.y[gj];
   }
   if (d.aug && ti == T - 1 && tj == T - 1 && tid == 0) {
     const int bn = n / GPB_NB;
-    if (!d.own_P || (bn % d.own_P == d.own_p && (bn / d.own_W) % d.own_Q == d.own_q)) d.A[n + (size_t)n * ld] = 0.0;
+    if (!d.own_P || (bn % d.own_P == d.own_p && (bn / d.own_W) % d.own_Q == d.own_q))
+      d.A[n + (size_t)(d.own_compact ? gpb_local_col(n, d.own_Q, d.own_q, d.own_W) : (long long)n) * ld] = 0.0;
   }
 }
 

@@ -130,10 +130,12 @@ class Plan:
     """B independent GPs evaluated together: assembly -> Cholesky (+ carried y) -> NLL -> inverse -> gradient."""
 
     def __init__(self, programs: Sequence[DeviceProgram], ns: Sequence[int], want_grad: bool = True,
-                 device: Optional[torch.device] = None, grid: Optional["ProcessGrid"] = None):
+                 device: Optional[torch.device] = None, grid: Optional["ProcessGrid"] = None,
+                 storage: str = "replicated"):
         """grid: a ProcessGrid makes this the distributed plan of ONE GP (2D block-cyclic block ownership, NCCL panel
         broadcasts; inverse and gradient split by block column).  Every rank of the grid must construct it and call
-        eval collectively."""
+        eval collectively.  storage = "columns" (1 x Q grids, want_grad = False): every rank keeps only the block
+        columns it owns - the likelihood of matrices that do not fit one GPU (STAGES_LML only)."""
         require_cuda()
         lib = _lib.load()
         self.lib = lib
@@ -147,7 +149,15 @@ class Plan:
         n_arr = (ctypes.c_int64 * self.B)(*self.ns)
         h = ctypes.c_void_p()
         self.grid = grid
-        if grid is not None:
+        self.storage = storage
+        if storage not in ("replicated", "columns"):
+            raise ValueError("storage must be 'replicated' or 'columns'")
+        if storage == "columns":
+            if grid is None or self.B != 1 or want_grad:
+                raise _lib.GpbError("column storage: one GP on a process grid, likelihood only (want_grad=False)")
+            _lib.check(lib.gpb_plan_create_dist_columns(self.programs[0].handle, self.ns[0], grid.handle, ctypes.byref(h)),
+                       "gpb_plan_create_dist_columns")
+        elif grid is not None:
             if self.B != 1:
                 raise _lib.GpbError("a distributed plan holds one GP")
             _lib.check(lib.gpb_plan_create_dist(self.programs[0].handle, self.ns[0], 1 if want_grad else 0, grid.handle,
@@ -179,6 +189,8 @@ class Plan:
         t = raw.view(torch.float64)
         n = self.ns[b]
         if which == BUF_A:
+            if self.storage == "columns":
+                return t.view(-1, ld.value)      # the packed own block columns (row r = local column r)
             return t.view(n + 1, ld.value)       # row r of this view = column r of the column-major matrix
         if which == BUF_KINV:
             return t.view(n, ld.value)

@@ -166,6 +166,12 @@ int gpb_dist_init(const unsigned char* id128, int rank, int world, int P, int Q,
 int gpb_dist_loopback_create(int world, int P, int Q, gpb_dist_t** out);
 void gpb_dist_destroy(gpb_dist_t* dist);
 int gpb_plan_create_dist(const gpb_program_t* prog, int64_t n, int want_grad, gpb_dist_t* dist, gpb_plan_t** out);
+/* The same likelihood (stages ASSEMBLE | POTRF | NLL only) with COLUMN STORAGE on a 1 x Q grid: every rank keeps only the
+ * block columns it owns (n^2 * 8 / Q bytes instead of the replicated n^2 * 8) plus a ring of three outer-panel buffers;
+ * an outer panel is broadcast in place from its owner's columns into the ring (no pack / unpack), and the log-determinant,
+ * z^T z and the first bad pivot are reduced over the ranks.  This is the plan for matrices that do not fit one GPU
+ * (n = 131072: 17 GB per rank on 8 GPUs instead of 137 GB); GPB_BUF_A of such a plan is the packed own columns.    */
+int gpb_plan_create_dist_columns(const gpb_program_t* prog, int64_t n, gpb_dist_t* dist, gpb_plan_t** out);
 /* host arithmetic of the layout (no GPU needed): owner rank of block (I, J); staging order of the n_tiles blocks of
  * panel k (tile t = block row k + t): process row o sends seg_count[o] tiles starting at slot seg_base[o], the first
  * of which is tile seg_first[o], the following ones P apart.                                                    */

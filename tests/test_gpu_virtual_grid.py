@@ -109,6 +109,83 @@ def run_case(eng, n, d, P, Q, check_oracle=True):
     return res
 
 
+def run_store_case(eng, n, d, Q, noise=1e-2):
+    """COLUMN STORAGE (gpb_plan_create_dist_columns): every virtual rank keeps only its own block columns; the
+    likelihood must equal the single-GPU plan's, on every rank bit for bit, with a smaller workspace"""
+    tree, hp, x, y = _problem(n, d, 11 + n)
+    prog = eng.DeviceProgram.get(tree, d, False, 1)
+    ref = eng.Plan([prog], [n], want_grad=False)
+    ref.set_data(0, torch.tensor(x), torch.tensor(y)); ref.set_hp(0, hp, noise)
+    ref.eval(eng.STAGES_LML)
+    torch.cuda.synchronize()
+    nll_ref, _, info_ref = ref.results()
+    vg = eng.VirtualGrid(1, Q)
+    plans = [eng.Plan([prog], [n], want_grad=False, grid=vg.ranks[r], storage="columns") for r in range(Q)]
+    rep_bytes = eng.Plan([prog], [n], want_grad=False, grid=vg.ranks[0]).ws_bytes
+
+    def work(r, grid):
+        dp = plans[r]
+        dp.set_data(0, torch.tensor(x), torch.tensor(y)); dp.set_hp(0, hp, noise)
+        out = []
+        for _ in range(3):                       # ring slots, events and the reduction scratch are reused
+            dp.eval(eng.STAGES_LML)
+            torch.cuda.current_stream().synchronize()
+            nll, _, info = dp.results()
+            out.append((float(nll[0]), int(info[0])))
+        nll_h, _, info_h = dp.eval_host([hp], [noise], [x], [y.reshape(-1)], stages=eng.STAGES_LML)
+        out.append((float(nll_h[0]), int(info_h[0])))
+        return out
+    res = vg.run(work)
+    for r, o in enumerate(res):
+        for nll, info in o:
+            assert info == int(info_ref[0]), (n, Q, r, info, info_ref)
+            if info == 0:
+                assert abs(nll - float(nll_ref[0])) <= LL_RTOL * abs(float(nll_ref[0])), (n, Q, r, nll, nll_ref)
+                assert nll == res[0][0][0], (n, Q, r)             # every rank, every repetition: the same bits
+            else:
+                assert np.isnan(nll)
+    if n >= 1000 and Q >= 2:
+        assert max(pl.ws_bytes for pl in plans) < rep_bytes, (plans[0].ws_bytes, rep_bytes)
+    return res
+
+
+@pytest.mark.parametrize("Q", [2, 3, 4])
+def test_column_storage_likelihood_matches_single_gpu_plan(Q):
+    eng = _eng()
+    run_store_case(eng, 1000, 1, Q)          # ragged last block
+    run_store_case(eng, 1024, 8, Q)          # the carried row opens a block column of its own
+    run_store_case(eng, 1409, 1, Q)          # odd number of blocks: ragged last group
+    run_store_case(eng, 385, 1, Q)           # fewer groups than ranks
+    run_store_case(eng, 700, 1, Q, noise=-5.0)   # not positive definite: the same info on every rank, NaN likelihood
+
+
+def test_column_storage_refuses_gradient_stages():
+    eng = _eng()
+    from gaussianprocessfundamentals_b200 import _lib
+    tree, hp, x, y = _problem(300, 1, 5)
+    prog = eng.DeviceProgram.get(tree, 1, False, 1)
+    vg = eng.VirtualGrid(1, 2)
+    with pytest.raises(_lib.GpbError):
+        eng.Plan([prog], [300], want_grad=True, grid=vg.ranks[0], storage="columns")
+    plans = [eng.Plan([prog], [300], want_grad=False, grid=vg.ranks[r], storage="columns") for r in range(2)]
+
+    def work(r, grid):
+        dp = plans[r]
+        dp.set_data(0, torch.tensor(x), torch.tensor(y)); dp.set_hp(0, hp, 1e-2)
+        dp.eval(eng.STAGES_LML)
+        refused = 0
+        for bit in (eng.STAGE_TRTRI, eng.STAGE_BACKSOLVE, eng.STAGE_GRAD):
+            try:
+                dp.eval(bit)
+            except _lib.GpbError:
+                refused += 1
+        return refused
+    assert vg.run(work) == [3, 3]
+    vg2 = eng.VirtualGrid(2, 1)
+    with pytest.raises(_lib.GpbError):
+        eng.Plan([prog], [300], want_grad=False, grid=vg2.ranks[0], storage="columns")   # needs a 1 x Q grid
+
+
 @pytest.mark.parametrize("P,Q", [(1, 2), (2, 1), (2, 2), (1, 3), (3, 2)])
 def test_virtual_grid_matches_single_gpu_plan(P, Q):
     eng = _eng()
@@ -203,11 +280,13 @@ def test_virtual_grid_column_group_widths_subprocess(ow):
 import sys
 sys.path.insert(0, %r)
 from gaussianprocessfundamentals_b200 import engine as eng
-from tests.test_gpu_virtual_grid import run_case
+from tests.test_gpu_virtual_grid import run_case, run_store_case
 for (P, Q) in [(1, 2), (1, 3), (1, 4)]:
     run_case(eng, 1100, 1, P, Q)
     run_case(eng, 1280, 8, P, Q, check_oracle=False)
     run_case(eng, 385, 1, P, Q, check_oracle=False)
+    run_store_case(eng, 1100, 1, Q)
+    run_store_case(eng, 1280, 8, Q)
 print("ok")
 """ % ROOT
     # ow = 1 also runs the un-overlapped exchange of W (one exchange after the inverse, W^T W as one launch)
