@@ -344,7 +344,7 @@ def run_dist(ctx, key, steps, warmup):
     from gaussianprocessfundamentals_b200 import engine as eng
     args, rank, world = ctx.args, ctx.rank, ctx.world
     w = WORKLOADS[key]
-    n, d = w["n"], w["d"]
+    n, d = (args.size if args.size else w["n"]), w["d"]
     want_grad = bool(w.get("grad", False))
     STAGES = eng.STAGES_LML_GRAD if want_grad else eng.STAGES_LML
     x, y, ell = make_c5(n, d)
@@ -353,7 +353,8 @@ def run_dist(ctx, key, steps, warmup):
     if world > 1:
         P, Q = (args.grid if args.grid else eng.ProcessGrid.default_shape(world))
         grid = eng.ProcessGrid(P, Q)
-    plan = eng.Plan([prog], [n], want_grad=want_grad, grid=grid)
+    storage = args.storage if (world > 1 and not want_grad) else "replicated"
+    plan = eng.Plan([prog], [n], want_grad=want_grad, grid=grid, storage=storage)
     plan.set_data(0, torch.tensor(x), torch.tensor(y))
     plan.set_hp(0, ell, 1e-2)
     ev, barrier = ctx.ev, ctx.barrier
@@ -406,6 +407,7 @@ def run_dist(ctx, key, steps, warmup):
     elapsed_ms, e2e_ms = red[0], red[1]
     for i, k_ in enumerate(keys):
         stage_ms[k_] = red[2 + i]
+    ws_gib = round(plan.ws_bytes / 2 ** 30, 2)
     del plan
     torch.cuda.empty_cache()
     if rank != 0:
@@ -418,7 +420,8 @@ def run_dist(ctx, key, steps, warmup):
         "unit": "evals/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dist_config(key, world, (grid.P, grid.Q) if grid else None),
+        "config": dict(dist_config(key, world, (grid.P, grid.Q) if grid else None), n=n, storage=storage,
+                       workspace_gib_per_rank=ws_gib),
         "e2e": {"value": steps / (e2e_ms * 1e-3), "unit": "evals/s",
                 "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + ell.nbytes + 8),
                 "d2h_bytes_per_step": 8 + 4 + 16 + (8 * (d + 1) if want_grad else 0),
@@ -673,6 +676,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--storage", default="replicated", choices=["replicated", "columns"],
+                    help="likelihood-only distributed workloads (c5, c5s) on N > 1 GPUs: 'columns' keeps only the own block "
+                         "columns on every rank (gpb_plan_create_dist_columns)")
+    ap.add_argument("--size", type=int, default=0, help="override the size of a one-large-GP workload (c5, c5s, c5g, m32kd)")
     ap.add_argument("--grid", type=lambda v: tuple(int(t) for t in v.split("x")), default=None,
                     help="process grid PxQ of the distributed workloads (default: ProcessGrid.default_shape)")
     args = ap.parse_args()

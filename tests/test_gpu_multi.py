@@ -82,6 +82,17 @@ def _dist_worker(rank, world, port, cases, out):
             dp.eval(eng.STAGES_LML)
             torch.cuda.synchronize()
             nll_d2 = dp.results()[0]
+            # column storage (1 x Q grids): every rank keeps only its own block columns, panels travel in place over NCCL
+            nll_cs, info_cs, ws_ratio = None, -1, 0.0
+            if P == 1:
+                cs = eng.Plan([prog], [n], want_grad=False, grid=grid, storage="columns")
+                cs.set_data(0, torch.tensor(x), torch.tensor(y)); cs.set_hp(0, hp, 1e-2)
+                for _ in range(2):
+                    cs.eval(eng.STAGES_LML)
+                    torch.cuda.synchronize()
+                nll_c, _, info_c = cs.results()
+                nll_cs, info_cs, ws_ratio = float(nll_c[0]), int(info_c[0]), cs.ws_bytes / dp.ws_bytes
+                del cs
             # host-buffer call
             nll_h, _, info_h = dp.eval_host([hp], [1e-2], [x], [y.reshape(-1)], stages=eng.STAGES_LML)
             # gradient stages: W = inv(L) and inv(K) split by block column, one all-reduce of the gradient
@@ -101,7 +112,8 @@ def _dist_worker(rank, world, port, cases, out):
             dpg.eval(eng.STAGES_LML_GRAD)
             torch.cuda.synchronize()
             g_d2 = dpg.results()[1]
-            res.append(dict(n=n, d=d, P=P, Q=Q, nll_ref=float(nll_ref[0]), nll=float(nll_d[0]), nll2=float(nll_d2[0]),
+            res.append(dict(n=n, d=d, P=P, Q=Q, nll_cs=nll_cs, info_cs=info_cs, ws_ratio=ws_ratio,
+                            nll_ref=float(nll_ref[0]), nll=float(nll_d[0]), nll2=float(nll_d2[0]),
                             nll_host=float(nll_h[0]), info=int(info_d[0]), info_ref=int(info_ref[0]), dL=dL, dz=dz,
                             Lmax=float(L_ref[tril].abs().max()), nll_grad_run=float(nll_g[0]), info_g=int(info_g[0]),
                             grad=[float(v) for v in g_d[0]], grad_ref=[float(v) for v in g_ref[0]],
@@ -167,6 +179,10 @@ def test_distributed_cholesky_matches_single_gpu(outer_blocks, monkeypatch):
             assert abs(r["nll"] - r["nll_ref"]) <= LL_RTOL * abs(r["nll_ref"]), tag
             assert r["nll2"] == r["nll"], tag
             assert r["nll_host"] == r["nll"], tag
+            if r["P"] == 1:    # column storage: same likelihood from a fraction of the workspace
+                assert r["info_cs"] == 0 and abs(r["nll_cs"] - r["nll_ref"]) <= LL_RTOL * abs(r["nll_ref"]), tag
+                if r["n"] >= 1000:
+                    assert r["ws_ratio"] < 0.8, tag
             assert r["dL"] <= 1e-12 * r["Lmax"], tag
             assert r["dz"] <= 1e-9, tag
             assert r["info_g"] == 0 and abs(r["nll_grad_run"] - r["nll_ref"]) <= LL_RTOL * abs(r["nll_ref"]), tag
@@ -178,13 +194,19 @@ def test_distributed_cholesky_matches_single_gpu(outer_blocks, monkeypatch):
         assert res[-1]["bad_info"] > 0 and res[-1]["bad_nll_isnan"]
     # every rank reports the same numbers
     for r0, r1 in zip(got[0][1], got[-1][1]):
+        r0, r1 = dict(r0), dict(r1)
+        r0.pop("ws_ratio", None); r1.pop("ws_ratio", None)     # the ranks own different numbers of block columns
         assert r0 == r1
     # against the CPU oracle (small case)
     r = got[0][1][0]
     tree, hp, x, y = _problem(r["n"], r["d"], 7 + r["n"])
     hpl = [np.asarray(v) for v in hp]
     want, _, _ = orc.nll_and_grad(tree, hpl, 1e-2, x, y, reference_distance=False)
-    assert abs(r["nll"] - want) <= LL_RTOL * abs(want)
+    # The strict 1e-10 comparison above is with the single-GPU plan (itself held to 1e-10 against oracle values frozen in
+    # the build container, tests/test_gpu_parity_sizes.py).  The LIVE oracle runs on the CPU of whatever box the test
+    # lands on, and its LAPACK result for this ill-conditioned composite kernel moves in the 10th digit from box to box
+    # (seen: 1.6e-10 on one pool box, 3e-12 on others), so it is held to 1e-8 here.
+    assert abs(r["nll"] - want) <= 1e-8 * abs(want)
 
 
 def _shard_worker(rank, world, port, out):
