@@ -7,21 +7,29 @@
 // BASELINE config 5 / SURVEY 8(e), second row.
 //
 // Factorisation.  2D block-cyclic OWNERSHIP of the 128 x 128 blocks of the lower triangle - block (I, J) is assembled
-// and updated by rank (I mod P) * Q + (J mod Q) - over REPLICATED storage: every rank holds the full (n+1) x ld
-// column-major workspace of the single-GPU plan, its own blocks are live, and each finished panel (block column k of L)
-// and inverted diagonal block is broadcast to all ranks, so that after the factorisation every rank holds the complete
-// L (the later stages read all of it).  The exchange per block column k is
-//   P == 1 : one grouped ncclBroadcast of the packed panel (diagonal block + all blocks below it) and inv(L_kk)
-//   P  > 1 : ncclBroadcast of {L_kk, inv(L_kk)} from the diagonal owner, then one grouped ncclBroadcast per process
-//            row of the panel blocks that row owns.
+// and updated by rank (I mod P) * Q + ((J / OW) mod Q), OW = dist_col_width(P) - in two storage layouts:
+//   * REPLICATED storage (gpb_plan_create_dist): every rank holds the full (n+1) x ld column-major workspace of the
+//     single-GPU plan, its own blocks are live, and each finished panel (+ inverted diagonal block) is broadcast to all
+//     ranks, so that after the factorisation every rank holds the complete L - the inverse and gradient stages read all of it;
+//   * COLUMN storage (gpb_plan_create_dist_columns, 1 x Q grids, likelihood only): every rank holds only its own block
+//     columns plus a ring of three outer-panel buffers (run_potrf_dist_store).
+// Drivers:
+//   run_potrf_dist_cols  (P == 1, the default grid 1 x N): block columns owned in groups of OW = 2; an outer panel is
+//                        factorised on its owner without any exchange and shipped with ONE broadcast on a
+//                        communication stream of its own; receivers post it only when the owner can be ready, so the
+//                        NCCL kernel does not spin on SMs the bulk update needs; look-ahead of depth 2.
+//   run_potrf_dist       (P > 1): single block columns; ncclBroadcast of {L_kk, inv(L_kk)} down the process column, then
+//                        one grouped ncclBroadcast per process row of the panel blocks that row owns.
+//   run_potrf_dist_store (column storage): the schedule of run_potrf_dist_cols, panels broadcast in place.
 // NVSwitch gives every pair of GPUs full bandwidth, so replicating the panel (n^2/2 doubles per rank over the whole
-// factorisation, 17 GB at n = 65536, ~25 ms at the measured 700 GB/s) is cheaper than the bookkeeping of row/column
-// communicators; the grid shape only balances the load (measured: 1 x N is fastest).  Panels travel tile-major through
-// two staging buffers.  Two panels are applied to the far trailing matrix together (k = 256) as on one GPU.
+// factorisation, 17 GB at n = 65536, ~25 ms at the measured 700 GB/s) is cheap; what limits the scaling at n = 32768 on
+// 8 GPUs is the serial chain factorise -> broadcast -> update of the next owner's columns.
+// Panels travel tile-major through two staging buffers (replicated storage).
 //
-// Streams: the critical path (diagonal block, panel, exchange, strip update, next diagonal column) runs on the plan's
-// high-priority stream, the bulk of the trailing update on the low-priority one (look-ahead).  CTAs of the bulk update
-// are one tile each: persistent CTAs kept every SM until the update ended and serialised the NCCL kernels behind it.
+// Streams: the critical path (diagonal block, panel, strip update, next group's columns) runs on the plan's
+// high-priority stream, the exchange on the communication stream, the second-next group's columns on the medium and the
+// bulk of the trailing update on the low-priority one.  CTAs of the bulk update are one tile each: persistent CTAs
+// kept every SM until the update ended and serialised the NCCL kernels behind it.
 //
 // Gradient stages: see the block comment above GeoDistTriDiag.
 #include <dlfcn.h>
